@@ -1,0 +1,145 @@
+"""ctypes binding of ``include/fiber_b200.h`` (libfiber_b200.so).
+
+This file *is* the reference-side binding a fiber maintainer would add: plain
+``ctypes``, no torch types.  There is no CPU fallback: if the shared library is missing or cannot be
+loaded, importing the engine raises immediately.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libfiber_b200.so")
+
+FBR_ABI_VERSION = 1
+
+# fbr_status
+FBR_OK, FBR_EINVAL, FBR_ECUDA, FBR_ENOMEM, FBR_ESTATE, FBR_ETIMEOUT, FBR_ETASK, FBR_ENODEV, FBR_ENOENT = \
+    0, -1, -2, -3, -4, -5, -6, -7, -8
+# fbr_result_kind
+FBR_RES_BYTES, FBR_RES_BOOL, FBR_RES_I64, FBR_RES_U32, FBR_RES_F64X2, FBR_RES_NONE = range(6)
+# body flags
+FBR_BODY_INDEX_ARG, FBR_BODY_NEEDS_SHARED, FBR_BODY_SUMMABLE = 0x1, 0x2, 0x4
+# pool flags
+FBR_POOL_TIMING = 0x1
+# map flags
+FBR_MAP, FBR_STARMAP, FBR_APPLY = 0x0, 0x1, 0x2
+FBR_ARGS_DEVICE, FBR_OUT_DEVICE, FBR_WANT_SUM, FBR_SHUFFLE, FBR_FULL_WINDOW, FBR_SHARED_HANDLE = \
+    0x10, 0x20, 0x40, 0x80, 0x100, 0x200
+# fbr_task_error
+FBR_TASK_OK, FBR_TASK_OVERFLOW, FBR_TASK_BADARG, FBR_TASK_FAULT = range(4)
+
+# every symbol include/fiber_b200.h declares (tests check the .so exports each of them)
+SYMBOLS = [
+    "fbr_abi_version", "fbr_last_error", "fbr_device_count",
+    "fbr_body_count", "fbr_body_info", "fbr_body_lookup",
+    "fbr_pool_create", "fbr_pool_close", "fbr_pool_terminate", "fbr_pool_join", "fbr_pool_destroy",
+    "fbr_pool_n_workers", "fbr_pool_worker_device",
+    "fbr_map_submit", "fbr_shared_put", "fbr_shared_drop",
+    "fbr_result_wait", "fbr_result_poll", "fbr_result_data", "fbr_result_release",
+    "fbr_host_alloc", "fbr_host_free", "fbr_device_alloc", "fbr_device_free",
+    "fbr_memcpy_h2d", "fbr_memcpy_d2h", "fbr_payload_fill_device",
+    "fbr_pool_stats", "fbr_pool_stats_reset",
+]
+
+
+class BodyInfo(ctypes.Structure):
+    _fields_ = [("func_id", ctypes.c_int32), ("arg_bytes", ctypes.c_uint32), ("result_bytes", ctypes.c_uint32),
+                ("result_kind", ctypes.c_uint32), ("flags", ctypes.c_uint32), ("unit_tasks", ctypes.c_uint32),
+                ("name", ctypes.c_char * 40)]
+
+
+class MapDesc(ctypes.Structure):
+    _fields_ = [("func_id", ctypes.c_int32), ("flags", ctypes.c_uint32), ("n_tasks", ctypes.c_uint64),
+                ("chunksize", ctypes.c_uint32), ("arg_stride", ctypes.c_uint32), ("args", ctypes.c_void_p),
+                ("index_start", ctypes.c_int64), ("index_step", ctypes.c_int64),
+                ("shared", ctypes.c_void_p), ("shared_bytes", ctypes.c_uint64), ("out", ctypes.c_void_p),
+                ("task_index_base", ctypes.c_uint64), ("shuffle_seed", ctypes.c_uint64)]
+
+
+class Result(ctypes.Structure):
+    _fields_ = [("seq", ctypes.c_uint64), ("n_tasks", ctypes.c_uint64), ("result_bytes", ctypes.c_uint32),
+                ("result_kind", ctypes.c_uint32), ("data", ctypes.c_void_p), ("sum", ctypes.c_int64),
+                ("err_code", ctypes.c_uint32), ("n_waves", ctypes.c_uint32), ("err_task", ctypes.c_uint64)]
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("tasks_submitted", ctypes.c_uint64), ("tasks_completed", ctypes.c_uint64),
+                ("units_dispatched", ctypes.c_uint64), ("dispatch_launches", ctypes.c_uint64),
+                ("gather_launches", ctypes.c_uint64), ("fill_launches", ctypes.c_uint64),
+                ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64),
+                ("dispatch_ms", ctypes.c_double), ("gather_ms", ctypes.c_double),
+                ("gather_bytes", ctypes.c_uint64), ("dispatch_bytes", ctypes.c_uint64)]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+class EngineError(RuntimeError):
+    """A libfiber_b200 call failed (``status`` is the negative ``fbr_status``)."""
+
+    def __init__(self, status, message):
+        super().__init__("%s (fbr_status %d)" % (message, status))
+        self.status = status
+
+
+_lib = None
+
+
+def load():
+    """Load libfiber_b200.so.  Fails loudly: this package has no CPU or eager fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "fiber_b200: %s is missing -- build it with `python -m fiber_b200.build` "
+            "(needs nvcc; there is no CPU fallback)" % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    vp, u64, i32, u32 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32
+    P = ctypes.POINTER
+    sig = {
+        "fbr_abi_version": (i32, []),
+        "fbr_last_error": (ctypes.c_char_p, []),
+        "fbr_device_count": (i32, [P(i32)]),
+        "fbr_body_count": (i32, [P(i32)]),
+        "fbr_body_info": (i32, [i32, P(BodyInfo)]),
+        "fbr_body_lookup": (i32, [ctypes.c_char_p, P(i32)]),
+        "fbr_pool_create": (i32, [i32, P(i32), u64, u32, P(vp)]),
+        "fbr_pool_close": (i32, [vp]),
+        "fbr_pool_terminate": (i32, [vp]),
+        "fbr_pool_join": (i32, [vp]),
+        "fbr_pool_destroy": (i32, [vp]),
+        "fbr_pool_n_workers": (i32, [vp, P(i32)]),
+        "fbr_pool_worker_device": (i32, [vp, i32, P(i32)]),
+        "fbr_map_submit": (i32, [vp, P(MapDesc), P(u64)]),
+        "fbr_shared_put": (i32, [vp, vp, u64, P(u64)]),
+        "fbr_shared_drop": (i32, [vp, u64]),
+        "fbr_result_wait": (i32, [vp, u64, i32, P(Result)]),
+        "fbr_result_poll": (i32, [vp, u64, P(u64)]),
+        "fbr_result_data": (i32, [vp, u64, P(vp)]),
+        "fbr_result_release": (i32, [vp, u64]),
+        "fbr_host_alloc": (i32, [vp, u64, P(vp)]),
+        "fbr_host_free": (i32, [vp, vp]),
+        "fbr_device_alloc": (i32, [vp, i32, u64, P(vp)]),
+        "fbr_device_free": (i32, [vp, i32, vp]),
+        "fbr_memcpy_h2d": (i32, [vp, i32, vp, vp, u64]),
+        "fbr_memcpy_d2h": (i32, [vp, i32, vp, vp, u64]),
+        "fbr_payload_fill_device": (i32, [vp, i32, vp, u64, u64]),
+        "fbr_pool_stats": (i32, [vp, P(Stats)]),
+        "fbr_pool_stats_reset": (i32, [vp]),
+    }
+    assert sorted(sig) == sorted(SYMBOLS)
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    if L.fbr_abi_version() != FBR_ABI_VERSION:
+        raise RuntimeError("fiber_b200: ABI mismatch, rebuild with `python -m fiber_b200.build --force`")
+    _lib = L
+    return L
+
+
+def check(status):
+    if status != FBR_OK:
+        raise EngineError(status, load().fbr_last_error().decode("utf-8", "replace"))
+    return status

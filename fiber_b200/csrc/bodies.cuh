@@ -1,0 +1,197 @@
+// bodies.cuh -- the mapped function bodies, as device code.
+//
+// In the reference the mapped function is a pickled Python callable executed by the worker at
+// fiber/pool.py:806,809,820.  Here each supported callable has a compiled-in device body selected
+// by func_id in the task record.  Three execution shapes:
+//   * ThreadBody  : one thread per task, results packed 16 B per store       (square, pi, ...)
+//   * RecordBody  : one CTA streams 4 KB records through registers            (payload_map)
+//   * ReduceBody  : a warp / CTA cooperates on one task and emits a scalar    (checksum, parzen)
+// Integer/byte bodies are bit-exact against oracle/bodies.py; parzen_f32 carries the north-star's
+// stated fp32 tolerance, parzen_f64 is bit-exact.
+#pragma once
+#include <stdint.h>
+
+namespace fbr {
+
+enum FuncId : int32_t {
+    F_SQUARE_I64 = 0,        // tests/test_pool.py:18-19   f(x) = x*x
+    F_MUL2_I64 = 1,          // tests/test_pool.py:21-22   f2(x, y) = x*y
+    F_SQUARE_SCALE_I64 = 2,  // tests/test_pool.py:24-25   fy(x, y=1) = x*x*y
+    F_IDENTITY_I64 = 3,      // tests/test_pool.py:60-68   random_error_worker's return value
+    F_PI_INSIDE_DET = 4,     // examples/pi_estimation.py:9-11 (deterministic restatement)
+    F_PARZEN_F32 = 5,        // examples/parzen_estimation.py:6-15, fp32 window test
+    F_PARZEN_F64 = 6,        // same, fp64 window test (bit-exact k_n)
+    F_PAYLOAD_MAP_4K = 7,    // BASELINE.json config 4: 4 KB record -> 4 KB record
+    F_PAYLOAD_CHECKSUM_4K = 8,  // 4 KB record -> u32
+    F_SLEEP_F64 = 9,         // tests/test_pool.py:56-57   sleep_worker(duration) -> None
+    F_FAULT_IDENTITY_I64 = 10,  // identity with injected faults (resilient pool tests)
+    F_COUNT = 11
+};
+
+enum TaskError : uint32_t { TASK_OK = 0, TASK_OVERFLOW = 1, TASK_BADARG = 2, TASK_FAULT = 3 };
+
+// Lowest failing task wins, like the first exception a reference worker would have raised on the
+// lowest index.  Packed as (task_index << 8 | code) so a single atomicMin orders by index.
+// A TASK_FAULT is different: it models a worker *dying* inside a chunk (tests/test_pool.py:60-68):
+// the whole claim unit is marked lost in its ring-slot header and the resilient host layer
+// re-dispatches it (fiber/pool.py:1635-1654), so it only raises the CTA-local unit_fault flag.
+struct ErrSink {
+    unsigned long long* word;  // device, initialised to ~0ull
+    int* unit_fault;           // shared memory, one per CTA
+    __device__ __forceinline__ void report(uint32_t code, uint64_t task_index) const {
+        if (code == TASK_FAULT) { *unit_fault = 1; return; }
+        atomicMin(word, (unsigned long long)((task_index << 8) | (uint64_t)code));
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// checked int64 arithmetic: Python ints are unbounded, so overflow must fail loudly, not wrap.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int64_t mul_i64_checked(int64_t a, int64_t b, bool& ovf) {
+    int64_t lo = a * b;  // wraps
+    int64_t hi = __mul64hi(a, b);
+    ovf |= (hi != (lo >> 63));
+    return lo;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Random123).  Matches oracle/bodies.py:philox4x32_10 bit for bit.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3,
+                                              uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+
+// examples/pi_estimation.py:9-11 with random.random() replaced by one Philox block keyed by p
+// (oracle/bodies.py:pi_inside_det).  x*x + y*y < 1 is evaluated as three separately rounded
+// float64 operations (__dmul_rn/__dadd_rn forbid FMA contraction) exactly as CPython does.
+__device__ __forceinline__ uint8_t pi_inside_det(int64_t p) {
+    uint32_t c0 = (uint32_t)((uint64_t)p), c1 = (uint32_t)((uint64_t)p >> 32), c2 = 0u, c3 = 0u;
+    philox4x32_10(c0, c1, c2, c3, 0xF1BE5EEDu, 0u);
+    // (a>>5)*2^26 + (b>>6) is an exact 53-bit integer; the division by 2^53 is exact.
+    const double x = __dmul_rn((double)(((uint64_t)(c0 >> 5) << 26) | (uint64_t)(c1 >> 6)), 0x1.0p-53);
+    const double y = __dmul_rn((double)(((uint64_t)(c2 >> 5) << 26) | (uint64_t)(c3 >> 6)), 0x1.0p-53);
+    return __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)) < 1.0 ? 1 : 0;
+}
+
+// SplitMix64 finaliser; oracle/bodies.py:splitmix64.
+__device__ __host__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    uint64_t z = x + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+constexpr uint32_t kPayloadWords = 1024;
+constexpr uint32_t kPayloadBytes = 4096;
+constexpr uint64_t kPayloadSeed = 0xF1BE5ull;
+constexpr uint32_t kPayloadMul = 2654435761u;
+
+// ================================================================================================
+// ThreadBody concept:  struct { using Arg; using Res; static Res run(const Arg&, uint64_t gidx, const ErrSink&, uint32_t attempt) }
+//   Arg is loaded from the argument ring, or (kIndexArg && arg_stride==0) synthesised from the
+//   task index: arg = index_start + i*index_step (a Python range()).
+// ================================================================================================
+struct I64x2 { int64_t x, y; };
+
+struct SquareI64 {
+    using Arg = int64_t; using Res = int64_t;
+    static constexpr bool kIndexArg = true;
+    __device__ static __forceinline__ Res run(const Arg& a, uint64_t gidx, const ErrSink& es, uint32_t) {
+        bool ovf = false;
+        const int64_t r = mul_i64_checked(a, a, ovf);
+        if (ovf) es.report(TASK_OVERFLOW, gidx);
+        return r;
+    }
+};
+struct Mul2I64 {
+    using Arg = I64x2; using Res = int64_t;
+    static constexpr bool kIndexArg = false;
+    __device__ static __forceinline__ Res run(const Arg& a, uint64_t gidx, const ErrSink& es, uint32_t) {
+        bool ovf = false;
+        const int64_t r = mul_i64_checked(a.x, a.y, ovf);
+        if (ovf) es.report(TASK_OVERFLOW, gidx);
+        return r;
+    }
+};
+struct SquareScaleI64 {
+    using Arg = I64x2; using Res = int64_t;
+    static constexpr bool kIndexArg = false;
+    __device__ static __forceinline__ Res run(const Arg& a, uint64_t gidx, const ErrSink& es, uint32_t) {
+        bool ovf = false;
+        const int64_t r = mul_i64_checked(mul_i64_checked(a.x, a.x, ovf), a.y, ovf);
+        if (ovf) es.report(TASK_OVERFLOW, gidx);
+        return r;
+    }
+};
+struct IdentityI64 {
+    using Arg = int64_t; using Res = int64_t;
+    static constexpr bool kIndexArg = true;
+    __device__ static __forceinline__ Res run(const Arg& a, uint64_t, const ErrSink&, uint32_t) { return a; }
+};
+// Identity whose tasks "kill their worker" with probability ~5 % per attempt, as
+// random_error_worker does (tests/test_pool.py:60-68).  The attempt number is carried in the
+// task record flags so a re-dispatched unit draws fresh faults.
+struct FaultIdentityI64 {
+    using Arg = int64_t; using Res = int64_t;
+    static constexpr bool kIndexArg = true;
+    __device__ static __forceinline__ Res run(const Arg& a, uint64_t gidx, const ErrSink& es, uint32_t attempt) {
+        const uint64_t h = splitmix64((gidx << 8) ^ (uint64_t)attempt ^ 0xFA17ull);
+        if ((h % 100ull) < 5ull) es.report(TASK_FAULT, gidx);
+        return a;
+    }
+};
+struct PiInsideDet {
+    using Arg = int64_t; using Res = uint8_t;
+    static constexpr bool kIndexArg = true;
+    __device__ static __forceinline__ Res run(const Arg& a, uint64_t, const ErrSink&, uint32_t) { return pi_inside_det(a); }
+};
+// sleep_worker(duration): busy-wait on the global nanosecond timer; returns None (one pad byte).
+struct SleepF64 {
+    using Arg = double; using Res = uint8_t;
+    static constexpr bool kIndexArg = false;
+    __device__ static __forceinline__ Res run(const Arg& a, uint64_t gidx, const ErrSink& es, uint32_t) {
+        if (!(a >= 0.0) || a > 10.0) { es.report(TASK_BADARG, gidx); return 0; }
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        const unsigned long long dur = (unsigned long long)(a * 1e9);
+        do {
+            __nanosleep(1000);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        } while (t1 - t0 < dur);
+        return 0;
+    }
+};
+
+// ================================================================================================
+// Parzen window (examples/parzen_estimation.py:6-15).  Shared block layout (host writes it once,
+// it is broadcast to every task instead of being pickled 102 times):
+//   struct ParzenShared { u32 n_samples; u32 dims; u32 power; u32 elem_bytes; f64 point_x[8]; }
+//   followed (at byte 80) by samples[n_samples][dims] in f32 or f64.
+// Per-task argument: h (f64).  Result: (h, (k_n / n) / h**power) as two f64.
+// ================================================================================================
+struct ParzenShared {
+    uint32_t n_samples, dims, power, elem_bytes;
+    double point_x[8];
+};
+static_assert(sizeof(ParzenShared) == 80, "layout is part of the ABI");
+
+template <typename T>
+__device__ __forceinline__ bool parzen_inside(const T* __restrict__ row, const ParzenShared& sh, T h) {
+    bool inside = true;
+    for (uint32_t d = 0; d < sh.dims; ++d) {
+        // (point_x - x) / h with IEEE division, then `abs(q) > 1/2` breaks (reference lines 9-12);
+        // written as !(|q| > 0.5) so a NaN counts as inside exactly like the reference.
+        const T q = ((T)sh.point_x[d] - row[d]) / h;
+        inside = inside && !(fabs(q) > (T)0.5);
+    }
+    return inside;
+}
+
+}  // namespace fbr

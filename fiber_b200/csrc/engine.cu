@@ -1,0 +1,965 @@
+// engine.cu -- host side of libfiber_b200.so: pool object, per-GPU workers, rings, wave pipeline,
+// and the extern "C" entry points declared in include/fiber_b200.h.
+//
+// One worker == one CUDA device (the GPU analogue of one job-backed worker process,
+// fiber/pool.py:1009-1057 + fiber/local_backend.py:37-42) with
+//   * three streams: copy-in (task records + arguments), compute (dispatch + gather), copy-out;
+//   * a pinned host task ring and its device mirror (fixed-layout TaskRecord, cudaMemcpyAsync);
+//   * a device result ring (payload arena + one SlotHeader per claim unit);
+//   * double-buffered device staging for host-resident arguments and ordered output.
+// A map is cut into waves that fit the rings; wave w+1's copy-in and wave w-1's copy-out overlap
+// wave w's kernels.  No host thread is needed: ordering is carried by stream events, completion
+// by events the caller waits on (fbr_result_wait / fbr_result_poll).
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <chrono>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/fiber_b200.h"
+#include "kernels.cuh"
+
+using namespace fbr;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CK(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(FBR_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// body table
+// ------------------------------------------------------------------------------------------------
+typedef void (*launch_fn)(const WaveParams&, int grid, cudaStream_t);
+
+template <class B>
+static void launch_thread(const WaveParams& wp, int grid, cudaStream_t s) {
+    dispatch_thread_kernel<B><<<grid, kThreads, 0, s>>>(wp);
+}
+static void launch_payload_map(const WaveParams& wp, int grid, cudaStream_t s) {
+    dispatch_payload_map_kernel<<<grid, kThreads, 0, s>>>(wp);
+}
+static void launch_payload_checksum(const WaveParams& wp, int grid, cudaStream_t s) {
+    dispatch_payload_checksum_kernel<<<grid, kThreads, 0, s>>>(wp);
+}
+template <typename T>
+static void launch_parzen(const WaveParams& wp, int grid, cudaStream_t s) {
+    dispatch_parzen_kernel<T><<<grid, kThreads, 0, s>>>(wp);
+}
+
+struct BodyEntry {
+    const char* name;
+    uint32_t arg_bytes, result_bytes, result_kind, flags, unit_tasks;
+    launch_fn launch;
+    const void* kernel;
+};
+
+static const BodyEntry kBodies[F_COUNT] = {
+    {"square_i64", 8, 8, FBR_RES_I64, FBR_BODY_INDEX_ARG | FBR_BODY_SUMMABLE, 4096, launch_thread<SquareI64>,
+     (const void*)dispatch_thread_kernel<SquareI64>},
+    {"mul2_i64", 16, 8, FBR_RES_I64, FBR_BODY_SUMMABLE, 4096, launch_thread<Mul2I64>,
+     (const void*)dispatch_thread_kernel<Mul2I64>},
+    {"square_scale_i64", 16, 8, FBR_RES_I64, FBR_BODY_SUMMABLE, 4096, launch_thread<SquareScaleI64>,
+     (const void*)dispatch_thread_kernel<SquareScaleI64>},
+    {"identity_i64", 8, 8, FBR_RES_I64, FBR_BODY_INDEX_ARG | FBR_BODY_SUMMABLE, 4096, launch_thread<IdentityI64>,
+     (const void*)dispatch_thread_kernel<IdentityI64>},
+    {"pi_inside_det", 8, 1, FBR_RES_BOOL, FBR_BODY_INDEX_ARG | FBR_BODY_SUMMABLE, 4096, launch_thread<PiInsideDet>,
+     (const void*)dispatch_thread_kernel<PiInsideDet>},
+    {"parzen_f32", 8, 16, FBR_RES_F64X2, FBR_BODY_NEEDS_SHARED, 1, launch_parzen<float>,
+     (const void*)dispatch_parzen_kernel<float>},
+    {"parzen_f64", 8, 16, FBR_RES_F64X2, FBR_BODY_NEEDS_SHARED, 1, launch_parzen<double>,
+     (const void*)dispatch_parzen_kernel<double>},
+    {"payload_map_4k", 4096, 4096, FBR_RES_BYTES, 0, 32, launch_payload_map, (const void*)dispatch_payload_map_kernel},
+    {"payload_checksum_4k", 4096, 4, FBR_RES_U32, FBR_BODY_SUMMABLE, 256, launch_payload_checksum,
+     (const void*)dispatch_payload_checksum_kernel},
+    {"sleep_f64", 8, 1, FBR_RES_NONE, 0, 1, launch_thread<SleepF64>, (const void*)dispatch_thread_kernel<SleepF64>},
+    {"fault_identity_i64", 8, 8, FBR_RES_I64, FBR_BODY_INDEX_ARG | FBR_BODY_SUMMABLE, 64, launch_thread<FaultIdentityI64>,
+     (const void*)dispatch_thread_kernel<FaultIdentityI64>},
+};
+
+// ------------------------------------------------------------------------------------------------
+// pool structures
+// ------------------------------------------------------------------------------------------------
+enum { ST_RUN = 0, ST_CLOSE = 1, ST_TERMINATE = 2 };
+constexpr int kRecWindows = 4;         // task-ring windows in flight
+constexpr uint32_t kRecCapacity = 65536;  // claim units per wave
+constexpr int kCtrlSlots = 1024;       // concurrent seqs per worker
+constexpr int kTickets = 64;
+
+struct SeqCtrl {              // per (seq, worker) control block, device + pinned mirror
+    long long sum;
+    unsigned long long err;   // (task_index << 8 | code), ~0 = none
+    uint32_t lost_count;
+    uint32_t pad;
+};
+static_assert(sizeof(SeqCtrl) == 24, "");
+
+struct LostUnit { uint64_t first; uint32_t count; uint32_t pad; };
+
+struct Worker {
+    int device = -1;
+    int sm_count = 0;
+    cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
+    TaskRecord* h_records = nullptr;   // pinned task ring: kRecWindows x kRecCapacity
+    TaskRecord* d_records = nullptr;   // device mirror
+    SlotHeader* d_headers = nullptr;   // kRecCapacity
+    uint8_t* d_ring = nullptr;         // result ring arena (ring_bytes)
+    uint8_t* d_args[2] = {nullptr, nullptr};
+    uint8_t* d_out[2] = {nullptr, nullptr};
+    uint32_t* d_tickets = nullptr;
+    SeqCtrl* d_ctrl = nullptr;
+    SeqCtrl* h_ctrl = nullptr;         // pinned: [0,kCtrlSlots) results, [kCtrlSlots] init pattern
+    cudaEvent_t ev_rec_h2d[kRecWindows];   // window's H2D finished (host may rewrite the pinned window)
+    cudaEvent_t ev_comp[kRecWindows];      // wave's kernels finished (device window / arg half reusable)
+    cudaEvent_t ev_out[2];                 // out half's D2H finished
+    uint64_t wave_no = 0;
+    int occ[F_COUNT];
+    int occ_gather = 1, occ_fill = 1;
+    std::vector<bool> ctrl_used;
+};
+
+struct TimedPair { cudaEvent_t a, b; };
+
+struct SeqPart {
+    int worker = 0;
+    uint64_t first = 0, count = 0;        // task block of this worker inside the map
+    int ctrl_slot = -1;
+    cudaEvent_t done = nullptr;
+    std::vector<cudaEvent_t> wave_done;
+    std::vector<uint64_t> wave_cum;       // tasks finished once wave i is done
+    std::vector<TimedPair> t_dispatch, t_gather;
+    void* d_shared_tmp = nullptr;         // per-seq device copy of a host shared block
+    void* d_window = nullptr;             // FULL_WINDOW device output
+};
+
+struct SeqState {
+    uint64_t seq = 0, n_tasks = 0;
+    int func_id = 0;
+    uint32_t flags = 0, result_bytes = 0, result_kind = 0;
+    void* out = nullptr;
+    bool own_out = false;
+    bool finished = false;
+    int64_t sum = 0;
+    uint32_t err_code = 0;
+    uint64_t err_task = 0;
+    uint32_t n_waves = 0;
+    std::vector<SeqPart> parts;
+};
+
+struct SharedBlock {
+    uint64_t bytes = 0;
+    std::vector<void*> d_ptr;  // per worker
+};
+
+struct fbr_pool {
+    std::mutex mu;
+    int state = ST_RUN;
+    uint32_t flags = 0;
+    uint64_t ring_bytes = 0;
+    std::vector<Worker> workers;
+    uint64_t next_seq = 0;
+    std::unordered_map<uint64_t, std::unique_ptr<SeqState>> seqs;
+    std::unordered_map<uint64_t, SharedBlock> shared;
+    uint64_t next_shared = 1;
+    // pinned host segment cache (size class -> free blocks), and live blocks -> class
+    std::unordered_map<uint64_t, std::vector<void*>> pin_free;
+    std::unordered_map<void*, uint64_t> pin_live;
+    fbr_stats_t stats;
+};
+
+// ------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------
+static uint64_t round_up(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
+
+static uint64_t pin_class(uint64_t bytes) {
+    uint64_t c = 4096;
+    while (c < bytes) c <<= 1;
+    return c;
+}
+
+static int pinned_acquire(fbr_pool* p, uint64_t bytes, void** out) {
+    const uint64_t c = pin_class(bytes ? bytes : 1);
+    auto& fl = p->pin_free[c];
+    void* ptr = nullptr;
+    if (!fl.empty()) {
+        ptr = fl.back();
+        fl.pop_back();
+    } else {
+        CK(cudaHostAlloc(&ptr, c, cudaHostAllocPortable));
+    }
+    p->pin_live[ptr] = c;
+    *out = ptr;
+    return FBR_OK;
+}
+
+static void pinned_release(fbr_pool* p, void* ptr) {
+    auto it = p->pin_live.find(ptr);
+    if (it == p->pin_live.end()) return;
+    p->pin_free[it->second].push_back(ptr);
+    p->pin_live.erase(it);
+}
+
+static int worker_init(fbr_pool* p, Worker& w, int device) {
+    w.device = device;
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(FBR_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    w.sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&w.s_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&w.s_comp, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&w.s_out, cudaStreamNonBlocking));
+    CK(cudaHostAlloc((void**)&w.h_records, sizeof(TaskRecord) * kRecCapacity * kRecWindows, cudaHostAllocPortable));
+    CK(cudaMalloc((void**)&w.d_records, sizeof(TaskRecord) * kRecCapacity * kRecWindows));
+    CK(cudaMalloc((void**)&w.d_headers, sizeof(SlotHeader) * kRecCapacity));
+    CK(cudaMalloc((void**)&w.d_ring, p->ring_bytes));
+    CK(cudaMalloc((void**)&w.d_tickets, sizeof(uint32_t) * kTickets));
+    CK(cudaMemset(w.d_tickets, 0, sizeof(uint32_t) * kTickets));
+    CK(cudaMalloc((void**)&w.d_ctrl, sizeof(SeqCtrl) * kCtrlSlots));
+    CK(cudaHostAlloc((void**)&w.h_ctrl, sizeof(SeqCtrl) * (kCtrlSlots + 1), cudaHostAllocPortable));
+    w.h_ctrl[kCtrlSlots] = SeqCtrl{0, ~0ull, 0u, 0u};
+    w.ctrl_used.assign(kCtrlSlots, false);
+    for (int i = 0; i < kRecWindows; ++i) {
+        CK(cudaEventCreateWithFlags(&w.ev_rec_h2d[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&w.ev_comp[i], cudaEventDisableTiming));
+    }
+    for (int i = 0; i < 2; ++i) CK(cudaEventCreateWithFlags(&w.ev_out[i], cudaEventDisableTiming));
+    for (int f = 0; f < F_COUNT; ++f) {
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kBodies[f].kernel, kThreads, 0));
+        w.occ[f] = occ > 0 ? occ : 1;
+    }
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w.occ_gather, (const void*)gather_ordered_kernel<false>, kThreads, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w.occ_fill, (const void*)payload_fill_kernel, kThreads, 0));
+    if (w.occ_gather < 1) w.occ_gather = 1;
+    if (w.occ_fill < 1) w.occ_fill = 1;
+    CK(cudaDeviceSynchronize());
+    return FBR_OK;
+}
+
+static void worker_destroy(Worker& w) {
+    if (w.device < 0) return;
+    cudaSetDevice(w.device);
+    cudaDeviceSynchronize();
+    if (w.s_in) cudaStreamDestroy(w.s_in);
+    if (w.s_comp) cudaStreamDestroy(w.s_comp);
+    if (w.s_out) cudaStreamDestroy(w.s_out);
+    cudaFreeHost(w.h_records);
+    cudaFree(w.d_records);
+    cudaFree(w.d_headers);
+    cudaFree(w.d_ring);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(w.d_args[i]);
+        cudaFree(w.d_out[i]);
+    }
+    cudaFree(w.d_tickets);
+    cudaFree(w.d_ctrl);
+    cudaFreeHost(w.h_ctrl);
+    for (int i = 0; i < kRecWindows; ++i) {
+        cudaEventDestroy(w.ev_rec_h2d[i]);
+        cudaEventDestroy(w.ev_comp[i]);
+    }
+    for (int i = 0; i < 2; ++i) cudaEventDestroy(w.ev_out[i]);
+    w.device = -1;
+}
+
+// Claim-unit size: near the body's preferred size, a multiple of the API chunksize when the chunk
+// is smaller (so chunk boundaries coincide with unit boundaries), and a multiple of 16/R tasks so
+// every full slot is 16 B aligned on both sides of the gather.
+static uint32_t pick_unit(const BodyEntry& b, uint32_t chunksize, uint64_t n_tasks, int sm_count) {
+    uint32_t pref = b.unit_tasks;
+    if (pref == 1) return 1;
+    // small maps: shrink the unit so the work still spreads over the SMs
+    while (pref > 256 && (uint64_t)pref * (uint64_t)sm_count > n_tasks) pref >>= 1;
+    const uint32_t align = b.result_bytes < 16 ? 16u / b.result_bytes : 1u;
+    uint32_t unit = pref;
+    if (chunksize <= pref) {
+        uint32_t m = chunksize;  // lcm(chunksize, align)
+        while (m % align) m += chunksize;
+        if (m <= 2 * pref) unit = std::max(m, pref / m * m);
+    }
+    unit = (uint32_t)round_up(unit, align);
+    return unit;
+}
+
+static void shuffle_records(TaskRecord* r, uint32_t n, uint64_t seed) {
+    for (uint32_t i = n; i > 1; --i) {
+        seed = splitmix64(seed);
+        const uint32_t j = (uint32_t)(seed % i);
+        std::swap(r[i - 1], r[j]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// wave pipeline for one worker's block of one map
+// ------------------------------------------------------------------------------------------------
+static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const fbr_map_desc_t& d, const BodyEntry& body) {
+    Worker& w = p->workers[part.worker];
+    CK(cudaSetDevice(w.device));
+    const uint32_t R = body.result_bytes;
+    const bool args_dev = (d.flags & FBR_ARGS_DEVICE) != 0;
+    const bool out_dev = (d.flags & FBR_OUT_DEVICE) != 0;
+    const bool full_window = out_dev || (d.flags & FBR_FULL_WINDOW);
+    const bool host_args = d.arg_stride != 0 && !args_dev;
+    const bool timing = (p->flags & FBR_POOL_TIMING) != 0;
+    const uint32_t cs = d.chunksize ? d.chunksize : 32u;
+    const uint32_t unit = pick_unit(body, cs, part.count, w.sm_count);
+    const uint32_t slot_stride = (uint32_t)round_up((uint64_t)unit * R, 16);
+
+    // control block
+    int slot = -1;
+    for (int i = 0; i < kCtrlSlots; ++i)
+        if (!w.ctrl_used[i]) { slot = i; break; }
+    if (slot < 0) return fail(FBR_ENOMEM, "more than %d maps in flight on worker %d", kCtrlSlots, part.worker);
+    w.ctrl_used[slot] = true;
+    part.ctrl_slot = slot;
+    CK(cudaMemcpyAsync(&w.d_ctrl[slot], &w.h_ctrl[kCtrlSlots], sizeof(SeqCtrl), cudaMemcpyHostToDevice, w.s_in));
+
+    // shared (broadcast) block
+    const uint8_t* d_shared = nullptr;
+    if (d.shared != nullptr && d.shared_bytes) {
+        if (d.flags & FBR_SHARED_HANDLE) {
+            auto it = p->shared.find((uint64_t)(uintptr_t)d.shared);
+            if (it == p->shared.end()) return fail(FBR_ENOENT, "unknown shared handle");
+            d_shared = (const uint8_t*)it->second.d_ptr[part.worker];
+        } else if (args_dev) {
+            d_shared = (const uint8_t*)d.shared;
+        } else {
+            CK(cudaMalloc(&part.d_shared_tmp, d.shared_bytes));
+            CK(cudaMemcpyAsync(part.d_shared_tmp, d.shared, d.shared_bytes, cudaMemcpyHostToDevice, w.s_in));
+            p->stats.h2d_bytes += d.shared_bytes;
+            d_shared = (const uint8_t*)part.d_shared_tmp;
+        }
+    }
+
+    // wave capacity in claim units
+    uint64_t units_cap = std::min<uint64_t>(kRecCapacity, p->ring_bytes / slot_stride);
+    if (host_args) units_cap = std::min<uint64_t>(units_cap, p->ring_bytes / ((uint64_t)unit * d.arg_stride));
+    if (!full_window) units_cap = std::min<uint64_t>(units_cap, p->ring_bytes / ((uint64_t)unit * R));
+    if (units_cap == 0) return fail(FBR_ENOMEM, "ring_bytes=%llu too small for one claim unit of %u tasks", (unsigned long long)p->ring_bytes, unit);
+    const uint64_t wave_tasks_cap = units_cap * unit;
+
+    // staging
+    if (host_args)
+        for (int i = 0; i < 2; ++i)
+            if (!w.d_args[i]) CK(cudaMalloc((void**)&w.d_args[i], p->ring_bytes));
+    if (!full_window)
+        for (int i = 0; i < 2; ++i)
+            if (!w.d_out[i]) CK(cudaMalloc((void**)&w.d_out[i], p->ring_bytes));
+    uint8_t* window_base = nullptr;  // device output for FULL_WINDOW
+    if (full_window) {
+        if (out_dev) {
+            window_base = (uint8_t*)d.out + part.first * R;
+        } else {
+            CK(cudaMalloc(&part.d_window, std::max<uint64_t>(part.count * R, 16)));
+            window_base = (uint8_t*)part.d_window;
+        }
+    }
+
+    const bool want_sum = (d.flags & FBR_WANT_SUM) != 0;
+    uint32_t sum_kind = 0;
+    if (want_sum) {
+        if (body.result_kind == FBR_RES_BOOL) sum_kind = kSumBool;
+        else if (body.result_kind == FBR_RES_I64) sum_kind = kSumI64;
+        else if (body.result_kind == FBR_RES_U32) sum_kind = kSumU32;
+        else return fail(FBR_EINVAL, "body %s results cannot be summed", body.name);
+    }
+
+    uint64_t done_tasks = 0;
+    while (done_tasks < part.count) {
+        const uint64_t wt = std::min<uint64_t>(wave_tasks_cap, part.count - done_tasks);
+        const uint32_t n_units = (uint32_t)((wt + unit - 1) / unit);
+        const uint64_t wno = w.wave_no++;
+        const int rw = (int)(wno % kRecWindows);
+        const int half = (int)(wno & 1);
+        const uint64_t wave_first = part.first + done_tasks;  // map index of the wave's first task
+
+        // 1. task records into the pinned ring window (host may not overwrite a window whose
+        //    previous H2D is still in flight)
+        CK(cudaEventSynchronize(w.ev_rec_h2d[rw]));
+        TaskRecord* hrec = w.h_records + (size_t)rw * kRecCapacity;
+        for (uint32_t u = 0; u < n_units; ++u) {
+            const uint64_t off = (uint64_t)u * unit;
+            TaskRecord& r = hrec[u];
+            r.seq = (uint32_t)st.seq;
+            r.count = (uint32_t)std::min<uint64_t>(unit, wt - off);
+            r.first = wave_first + off;
+            r.arg_off = args_dev ? (wave_first + off) * (uint64_t)d.arg_stride : off * (uint64_t)d.arg_stride;
+            r.func_id = (uint32_t)st.func_id;
+            r.attempt = 0;
+        }
+        if (d.flags & FBR_SHUFFLE) shuffle_records(hrec, n_units, d.shuffle_seed ^ (wno * 0x9E3779B97F4A7C15ull));
+
+        // 2. copy-in stream: wait until the device window / arg half were consumed, then H2D
+        CK(cudaStreamWaitEvent(w.s_in, w.ev_comp[rw], 0));  // wave wno-4 kernels done (device window free)
+        if (wno >= 2) CK(cudaStreamWaitEvent(w.s_in, w.ev_comp[(wno - 2) % kRecWindows], 0));  // arg half free
+        TaskRecord* drec = w.d_records + (size_t)rw * kRecCapacity;
+        CK(cudaMemcpyAsync(drec, hrec, sizeof(TaskRecord) * n_units, cudaMemcpyHostToDevice, w.s_in));
+        p->stats.h2d_bytes += sizeof(TaskRecord) * n_units;
+        const uint8_t* wave_args = nullptr;
+        if (host_args) {
+            const uint64_t bytes = wt * d.arg_stride;
+            CK(cudaMemcpyAsync(w.d_args[half], (const uint8_t*)d.args + wave_first * (uint64_t)d.arg_stride, bytes,
+                               cudaMemcpyHostToDevice, w.s_in));
+            p->stats.h2d_bytes += bytes;
+            wave_args = w.d_args[half];
+        } else if (args_dev) {
+            wave_args = (const uint8_t*)d.args;
+        }
+        CK(cudaEventRecord(w.ev_rec_h2d[rw], w.s_in));
+
+        // 3. compute stream: dispatch + gather
+        CK(cudaStreamWaitEvent(w.s_comp, w.ev_rec_h2d[rw], 0));
+        if (!full_window) CK(cudaStreamWaitEvent(w.s_comp, w.ev_out[half], 0));  // out half drained
+        WaveParams wp;
+        wp.records = drec;
+        wp.headers = w.d_headers;
+        wp.ring = w.d_ring;
+        wp.ticket = w.d_tickets + (wno % kTickets);
+        wp.n_units = n_units;
+        wp.slot_stride = slot_stride;
+        wp.args = wave_args;
+        wp.arg_stride = d.arg_stride;
+        wp.index_start = d.index_start;
+        wp.index_step = d.index_step;
+        wp.index_base = d.task_index_base;
+        wp.shared = d_shared;
+        wp.shared_bytes = d.shared_bytes;
+        wp.err_word = &w.d_ctrl[slot].err;
+        const int grid_d = (int)std::min<uint64_t>(n_units, (uint64_t)w.sm_count * w.occ[st.func_id]);
+        TimedPair td{nullptr, nullptr}, tg{nullptr, nullptr};
+        if (timing) {
+            CK(cudaEventCreate(&td.a)); CK(cudaEventCreate(&td.b));
+            CK(cudaEventCreate(&tg.a)); CK(cudaEventCreate(&tg.b));
+            CK(cudaEventRecord(td.a, w.s_comp));
+        }
+        body.launch(wp, grid_d, w.s_comp);
+        CK(cudaGetLastError());
+        if (timing) { CK(cudaEventRecord(td.b, w.s_comp)); CK(cudaEventRecord(tg.a, w.s_comp)); }
+
+        GatherParams gp;
+        gp.headers = w.d_headers;
+        gp.ring = w.d_ring;
+        gp.n_units = n_units;
+        gp.slot_stride = slot_stride;
+        gp.result_bytes = R;
+        gp.sum_kind = sum_kind;
+        gp.out = full_window ? window_base : w.d_out[half];
+        gp.win_first = full_window ? part.first : wave_first;
+        gp.sum = &w.d_ctrl[slot].sum;
+        gp.ticket_to_reset = wp.ticket;
+        gp.lost_count = nullptr;
+        gp.lost_units = nullptr;
+        gp.lost_capacity = 0;
+        const uint64_t total_vec = (uint64_t)n_units * (slot_stride >> 4);
+        const int grid_g = (int)std::max<uint64_t>(1, std::min<uint64_t>((total_vec + kThreads * 4 - 1) / (kThreads * 4),
+                                                                          (uint64_t)w.sm_count * w.occ_gather));
+        if (sum_kind) gather_ordered_kernel<true><<<grid_g, kThreads, 0, w.s_comp>>>(gp);
+        else gather_ordered_kernel<false><<<grid_g, kThreads, 0, w.s_comp>>>(gp);
+        CK(cudaGetLastError());
+        if (timing) {
+            CK(cudaEventRecord(tg.b, w.s_comp));
+            part.t_dispatch.push_back(td);
+            part.t_gather.push_back(tg);
+        }
+        CK(cudaEventRecord(w.ev_comp[rw], w.s_comp));
+        p->stats.dispatch_launches++;
+        p->stats.gather_launches++;
+        p->stats.units_dispatched += n_units;
+        p->stats.gather_bytes += 2 * wt * R;
+        p->stats.dispatch_bytes += wt * ((uint64_t)(d.arg_stride ? body.arg_bytes : 0) + R);
+
+        // 4. copy-out stream
+        cudaEvent_t wd;
+        CK(cudaEventCreateWithFlags(&wd, cudaEventDisableTiming));
+        if (!full_window) {
+            CK(cudaStreamWaitEvent(w.s_out, w.ev_comp[rw], 0));
+            CK(cudaMemcpyAsync((uint8_t*)st.out + wave_first * R, w.d_out[half], wt * R, cudaMemcpyDeviceToHost, w.s_out));
+            p->stats.d2h_bytes += wt * R;
+            CK(cudaEventRecord(w.ev_out[half], w.s_out));
+            CK(cudaEventRecord(wd, w.s_out));
+        } else {
+            CK(cudaEventRecord(wd, w.s_comp));
+        }
+        done_tasks += wt;
+        part.wave_done.push_back(wd);
+        part.wave_cum.push_back(done_tasks);
+        st.n_waves++;
+    }
+
+    // tail: (FULL_WINDOW to host) one D2H of the whole block; control block back to the host
+    const int last_rw = (int)((w.wave_no - 1) % kRecWindows);
+    CK(cudaStreamWaitEvent(w.s_out, w.ev_comp[last_rw], 0));
+    if (full_window && !out_dev && part.count) {
+        CK(cudaMemcpyAsync((uint8_t*)st.out + part.first * R, window_base, part.count * R, cudaMemcpyDeviceToHost, w.s_out));
+        p->stats.d2h_bytes += part.count * R;
+    }
+    CK(cudaMemcpyAsync(&w.h_ctrl[slot], &w.d_ctrl[slot], sizeof(SeqCtrl), cudaMemcpyDeviceToHost, w.s_out));
+    CK(cudaEventCreateWithFlags(&part.done, cudaEventDisableTiming));
+    CK(cudaEventRecord(part.done, w.s_out));
+    return FBR_OK;
+}
+
+static void free_seq(fbr_pool* p, SeqState& st) {
+    for (auto& part : st.parts) {
+        Worker& w = p->workers[part.worker];
+        cudaSetDevice(w.device);
+        if (part.done) { cudaEventSynchronize(part.done); cudaEventDestroy(part.done); }
+        for (auto e : part.wave_done) cudaEventDestroy(e);
+        for (auto& t : part.t_dispatch) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+        for (auto& t : part.t_gather) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+        if (part.d_shared_tmp) cudaFree(part.d_shared_tmp);
+        if (part.d_window) cudaFree(part.d_window);
+        if (part.ctrl_slot >= 0) w.ctrl_used[part.ctrl_slot] = false;
+    }
+    if (st.own_out && st.out) pinned_release(p, st.out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// extern "C" API
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int fbr_abi_version(void) { return FBR_ABI_VERSION; }
+const char* fbr_last_error(void) { return g_err.c_str(); }
+
+int fbr_device_count(int* n) {
+    if (!n) return fail(FBR_EINVAL, "n is NULL");
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        *n = 0;
+        cudaGetLastError();
+        return fail(FBR_ENODEV, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    *n = c;
+    return FBR_OK;
+}
+
+int fbr_body_count(int* n) {
+    if (!n) return fail(FBR_EINVAL, "n is NULL");
+    *n = F_COUNT;
+    return FBR_OK;
+}
+
+int fbr_body_info(int func_id, fbr_body_info_t* info) {
+    if (!info || func_id < 0 || func_id >= F_COUNT) return fail(FBR_EINVAL, "bad func_id %d", func_id);
+    const BodyEntry& b = kBodies[func_id];
+    memset(info, 0, sizeof *info);
+    info->func_id = func_id;
+    info->arg_bytes = b.arg_bytes;
+    info->result_bytes = b.result_bytes;
+    info->result_kind = b.result_kind;
+    info->flags = b.flags;
+    info->unit_tasks = b.unit_tasks;
+    snprintf(info->name, sizeof info->name, "%s", b.name);
+    return FBR_OK;
+}
+
+int fbr_body_lookup(const char* name, int* func_id) {
+    if (!name || !func_id) return fail(FBR_EINVAL, "NULL argument");
+    for (int f = 0; f < F_COUNT; ++f)
+        if (strcmp(kBodies[f].name, name) == 0) { *func_id = f; return FBR_OK; }
+    return fail(FBR_ENOENT, "no device body named '%s' is compiled into libfiber_b200", name);
+}
+
+int fbr_pool_create(int n_workers, const int* device_ids, uint64_t ring_bytes, uint32_t flags, fbr_pool_t** out) {
+    if (!out || n_workers <= 0) return fail(FBR_EINVAL, "bad arguments");
+    int ndev = 0;
+    int rc = fbr_device_count(&ndev);
+    if (rc != FBR_OK) return rc;
+    if (ndev == 0) return fail(FBR_ENODEV, "no CUDA device visible; fiber_b200 has no CPU fallback");
+    std::unique_ptr<fbr_pool> p(new fbr_pool());
+    p->flags = flags;
+    p->ring_bytes = round_up(ring_bytes ? ring_bytes : (256ull << 20), 4096);
+    memset(&p->stats, 0, sizeof p->stats);
+    p->workers.resize(n_workers);
+    for (int i = 0; i < n_workers; ++i) {
+        const int dev = device_ids ? device_ids[i] : (i % ndev);
+        if (dev < 0 || dev >= ndev) return fail(FBR_EINVAL, "device id %d out of range (have %d)", dev, ndev);
+        for (int j = 0; j < i; ++j)
+            if (p->workers[j].device == dev) return fail(FBR_EINVAL, "device %d bound to two workers", dev);
+        rc = worker_init(p.get(), p->workers[i], dev);
+        if (rc != FBR_OK) {
+            for (auto& w : p->workers) worker_destroy(w);
+            return rc;
+        }
+    }
+    *out = p.release();
+    return FBR_OK;
+}
+
+int fbr_pool_n_workers(fbr_pool_t* p, int* n) {
+    if (!p || !n) return fail(FBR_EINVAL, "NULL argument");
+    *n = (int)p->workers.size();
+    return FBR_OK;
+}
+
+int fbr_pool_worker_device(fbr_pool_t* p, int worker, int* dev) {
+    if (!p || !dev || worker < 0 || worker >= (int)p->workers.size()) return fail(FBR_EINVAL, "bad worker");
+    *dev = p->workers[worker].device;
+    return FBR_OK;
+}
+
+int fbr_pool_close(fbr_pool_t* p) {
+    if (!p) return fail(FBR_EINVAL, "NULL pool");
+    std::lock_guard<std::mutex> g(p->mu);
+    if (p->state == ST_RUN) p->state = ST_CLOSE;
+    return FBR_OK;
+}
+
+int fbr_pool_terminate(fbr_pool_t* p) {
+    if (!p) return fail(FBR_EINVAL, "NULL pool");
+    std::lock_guard<std::mutex> g(p->mu);
+    p->state = ST_TERMINATE;
+    return FBR_OK;
+}
+
+int fbr_pool_join(fbr_pool_t* p) {
+    if (!p) return fail(FBR_EINVAL, "NULL pool");
+    std::lock_guard<std::mutex> g(p->mu);
+    if (p->state == ST_RUN) return fail(FBR_ESTATE, "join() before close()/terminate()");
+    for (auto& w : p->workers) {
+        CK(cudaSetDevice(w.device));
+        CK(cudaStreamSynchronize(w.s_in));
+        CK(cudaStreamSynchronize(w.s_comp));
+        CK(cudaStreamSynchronize(w.s_out));
+    }
+    return FBR_OK;
+}
+
+int fbr_pool_destroy(fbr_pool_t* p) {
+    if (!p) return FBR_OK;
+    {
+        std::lock_guard<std::mutex> g(p->mu);
+        for (auto& kv : p->seqs) free_seq(p, *kv.second);
+        p->seqs.clear();
+        for (auto& kv : p->shared)
+            for (size_t i = 0; i < kv.second.d_ptr.size(); ++i) {
+                cudaSetDevice(p->workers[i].device);
+                cudaFree(kv.second.d_ptr[i]);
+            }
+        for (auto& w : p->workers) worker_destroy(w);
+        for (auto& kv : p->pin_free)
+            for (void* q : kv.second) cudaFreeHost(q);
+        for (auto& kv : p->pin_live) cudaFreeHost(kv.first);
+    }
+    delete p;
+    return FBR_OK;
+}
+
+int fbr_shared_put(fbr_pool_t* p, const void* host, uint64_t bytes, uint64_t* handle) {
+    if (!p || !host || !bytes || !handle) return fail(FBR_EINVAL, "bad arguments");
+    std::lock_guard<std::mutex> g(p->mu);
+    SharedBlock sb;
+    sb.bytes = bytes;
+    for (auto& w : p->workers) {
+        CK(cudaSetDevice(w.device));
+        void* dptr = nullptr;
+        CK(cudaMalloc(&dptr, bytes));
+        CK(cudaMemcpyAsync(dptr, host, bytes, cudaMemcpyHostToDevice, w.s_in));
+        CK(cudaStreamSynchronize(w.s_in));
+        sb.d_ptr.push_back(dptr);
+        p->stats.h2d_bytes += bytes;
+    }
+    *handle = p->next_shared++;
+    p->shared[*handle] = sb;
+    return FBR_OK;
+}
+
+int fbr_shared_drop(fbr_pool_t* p, uint64_t handle) {
+    if (!p) return fail(FBR_EINVAL, "NULL pool");
+    std::lock_guard<std::mutex> g(p->mu);
+    auto it = p->shared.find(handle);
+    if (it == p->shared.end()) return fail(FBR_ENOENT, "unknown shared handle");
+    for (size_t i = 0; i < it->second.d_ptr.size(); ++i) {
+        cudaSetDevice(p->workers[i].device);
+        cudaDeviceSynchronize();
+        cudaFree(it->second.d_ptr[i]);
+    }
+    p->shared.erase(it);
+    return FBR_OK;
+}
+
+int fbr_map_submit(fbr_pool_t* p, const fbr_map_desc_t* d, uint64_t* seq_out) {
+    if (!p || !d || !seq_out) return fail(FBR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> g(p->mu);
+    if (p->state != ST_RUN) return fail(FBR_ESTATE, "Pool is not running");
+    if (d->func_id < 0 || d->func_id >= F_COUNT) return fail(FBR_EINVAL, "bad func_id %d", d->func_id);
+    const BodyEntry& body = kBodies[d->func_id];
+    const bool dev_mode = (d->flags & (FBR_ARGS_DEVICE | FBR_OUT_DEVICE)) != 0;
+    if (dev_mode && p->workers.size() != 1)
+        return fail(FBR_EINVAL, "device-resident args/out need a single-worker pool (one process per GPU)");
+    if (d->arg_stride == 0) {
+        if (!(body.flags & FBR_BODY_INDEX_ARG))
+            return fail(FBR_EINVAL, "body %s needs explicit argument records (arg_stride=0)", body.name);
+    } else {
+        if (d->arg_stride < body.arg_bytes || (d->arg_stride % 8) != 0)
+            return fail(FBR_EINVAL, "arg_stride %u invalid for body %s (arg_bytes %u)", d->arg_stride, body.name, body.arg_bytes);
+        if (d->n_tasks && !d->args) return fail(FBR_EINVAL, "args is NULL");
+        if (body.arg_bytes >= 16 && (d->arg_stride % 16 || ((uintptr_t)d->args % 16)))
+            return fail(FBR_EINVAL, "argument records of body %s must be 16-byte aligned", body.name);
+    }
+    if ((body.flags & FBR_BODY_NEEDS_SHARED) && (!d->shared || d->shared_bytes < sizeof(ParzenShared)))
+        return fail(FBR_EINVAL, "body %s needs a shared argument block", body.name);
+    if ((d->flags & FBR_OUT_DEVICE) && !d->out) return fail(FBR_EINVAL, "FBR_OUT_DEVICE without out");
+    if ((d->flags & FBR_WANT_SUM) && !(body.flags & FBR_BODY_SUMMABLE))
+        return fail(FBR_EINVAL, "body %s results cannot be summed", body.name);
+
+    std::unique_ptr<SeqState> st(new SeqState());
+    st->seq = ++p->next_seq;
+    st->n_tasks = d->n_tasks;
+    st->func_id = d->func_id;
+    st->flags = d->flags;
+    st->result_bytes = body.result_bytes;
+    st->result_kind = body.result_kind;
+    st->out = d->out;
+    if (!st->out && d->n_tasks) {
+        int rc = pinned_acquire(p, d->n_tasks * body.result_bytes, &st->out);
+        if (rc != FBR_OK) return rc;
+        st->own_out = true;
+    }
+
+    // contiguous task blocks per worker, cut on claim-unit boundaries (block partition ==
+    // PUSH round-robin with chunk = block)
+    const int nw = (int)p->workers.size();
+    const uint32_t cs = d->chunksize ? d->chunksize : 32u;
+    const uint32_t unit = pick_unit(body, cs, (d->n_tasks + nw - 1) / nw, p->workers[0].sm_count);
+    const uint64_t units_total = (d->n_tasks + unit - 1) / unit;
+    const uint64_t units_per = (units_total + nw - 1) / nw;
+    for (int wi = 0; wi < nw && d->n_tasks; ++wi) {
+        const uint64_t b0 = std::min<uint64_t>(d->n_tasks, (uint64_t)wi * units_per * unit);
+        const uint64_t b1 = std::min<uint64_t>(d->n_tasks, (uint64_t)(wi + 1) * units_per * unit);
+        if (b1 <= b0) continue;
+        SeqPart part;
+        part.worker = wi;
+        part.first = b0;
+        part.count = b1 - b0;
+        st->parts.push_back(part);
+    }
+    for (auto& part : st->parts) {
+        int rc = submit_part(p, *st, part, *d, body);
+        if (rc != FBR_OK) {
+            free_seq(p, *st);
+            return rc;
+        }
+    }
+    p->stats.tasks_submitted += d->n_tasks;
+    *seq_out = st->seq;
+    p->seqs[st->seq] = std::move(st);
+    return FBR_OK;
+}
+
+static void harvest(fbr_pool* p, SeqState& st) {
+    if (st.finished) return;
+    st.sum = 0;
+    unsigned long long err = ~0ull;
+    for (auto& part : st.parts) {
+        Worker& w = p->workers[part.worker];
+        const SeqCtrl& c = w.h_ctrl[part.ctrl_slot];
+        st.sum += c.sum;
+        err = std::min(err, c.err);
+        for (auto& t : part.t_dispatch) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) p->stats.dispatch_ms += ms;
+        }
+        for (auto& t : part.t_gather) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) p->stats.gather_ms += ms;
+        }
+    }
+    if (err != ~0ull) {
+        st.err_code = (uint32_t)(err & 0xff);
+        st.err_task = (uint64_t)(err >> 8);
+    }
+    st.finished = true;
+    p->stats.tasks_completed += st.n_tasks;
+}
+
+int fbr_result_wait(fbr_pool_t* p, uint64_t seq, int timeout_ms, fbr_result_t* res) {
+    if (!p || !res) return fail(FBR_EINVAL, "NULL argument");
+    std::vector<std::pair<int, cudaEvent_t>> evs;
+    {
+        std::lock_guard<std::mutex> g(p->mu);
+        auto it = p->seqs.find(seq);
+        if (it == p->seqs.end()) return fail(FBR_ENOENT, "unknown seq %llu", (unsigned long long)seq);
+        for (auto& part : it->second->parts) evs.push_back({p->workers[part.worker].device, part.done});
+    }
+    // block outside the pool lock so other threads can keep submitting
+    const auto deadline = std::chrono::steady_clock::now() + std::chrono::milliseconds(timeout_ms < 0 ? 0 : timeout_ms);
+    for (auto& e : evs) {
+        CK(cudaSetDevice(e.first));
+        if (timeout_ms < 0) {
+            CK(cudaEventSynchronize(e.second));
+        } else {
+            for (;;) {
+                cudaError_t q = cudaEventQuery(e.second);
+                if (q == cudaSuccess) break;
+                if (q != cudaErrorNotReady) return fail(FBR_ECUDA, "cudaEventQuery: %s", cudaGetErrorString(q));
+                if (std::chrono::steady_clock::now() >= deadline) return fail(FBR_ETIMEOUT, "timeout waiting for seq %llu", (unsigned long long)seq);
+                std::this_thread::sleep_for(std::chrono::microseconds(50));
+            }
+        }
+    }
+    std::lock_guard<std::mutex> g(p->mu);
+    auto it = p->seqs.find(seq);
+    if (it == p->seqs.end()) return fail(FBR_ENOENT, "seq released while waiting");
+    SeqState& st = *it->second;
+    harvest(p, st);
+    memset(res, 0, sizeof *res);
+    res->seq = seq;
+    res->n_tasks = st.n_tasks;
+    res->result_bytes = st.result_bytes;
+    res->result_kind = st.result_kind;
+    res->data = st.out;
+    res->sum = st.sum;
+    res->err_code = st.err_code;
+    res->err_task = st.err_task;
+    res->n_waves = st.n_waves;
+    if (st.err_code) return fail(FBR_ETASK, "task %llu failed with code %u in body %s", (unsigned long long)st.err_task, st.err_code, kBodies[st.func_id].name);
+    return FBR_OK;
+}
+
+int fbr_result_poll(fbr_pool_t* p, uint64_t seq, uint64_t* n_done) {
+    if (!p || !n_done) return fail(FBR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> g(p->mu);
+    auto it = p->seqs.find(seq);
+    if (it == p->seqs.end()) return fail(FBR_ENOENT, "unknown seq %llu", (unsigned long long)seq);
+    // ordered progress: tasks [0, n_done) are final.  Blocks are contiguous per worker, so count
+    // complete waves worker by worker and stop at the first incomplete one.
+    uint64_t done = 0;
+    for (auto& part : it->second->parts) {
+        CK(cudaSetDevice(p->workers[part.worker].device));
+        uint64_t part_done = 0;
+        for (size_t i = 0; i < part.wave_done.size(); ++i) {
+            if (cudaEventQuery(part.wave_done[i]) != cudaSuccess) break;
+            part_done = part.wave_cum[i];
+        }
+        cudaGetLastError();
+        done += part_done;
+        if (part_done < part.count) break;
+    }
+    *n_done = done;
+    return FBR_OK;
+}
+
+int fbr_result_data(fbr_pool_t* p, uint64_t seq, void** data) {
+    if (!p || !data) return fail(FBR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> g(p->mu);
+    auto it = p->seqs.find(seq);
+    if (it == p->seqs.end()) return fail(FBR_ENOENT, "unknown seq %llu", (unsigned long long)seq);
+    *data = it->second->out;
+    return FBR_OK;
+}
+
+int fbr_result_release(fbr_pool_t* p, uint64_t seq) {
+    if (!p) return fail(FBR_EINVAL, "NULL pool");
+    std::lock_guard<std::mutex> g(p->mu);
+    auto it = p->seqs.find(seq);
+    if (it == p->seqs.end()) return fail(FBR_ENOENT, "unknown seq %llu", (unsigned long long)seq);
+    harvest(p, *it->second);  // keeps the timing statistics of maps released without a wait
+    free_seq(p, *it->second);
+    p->seqs.erase(it);
+    return FBR_OK;
+}
+
+int fbr_host_alloc(fbr_pool_t* p, uint64_t bytes, void** ptr) {
+    if (!p || !ptr) return fail(FBR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> g(p->mu);
+    return pinned_acquire(p, bytes, ptr);
+}
+
+int fbr_host_free(fbr_pool_t* p, void* ptr) {
+    if (!p) return fail(FBR_EINVAL, "NULL pool");
+    std::lock_guard<std::mutex> g(p->mu);
+    pinned_release(p, ptr);
+    return FBR_OK;
+}
+
+int fbr_device_alloc(fbr_pool_t* p, int worker, uint64_t bytes, void** dptr) {
+    if (!p || !dptr || worker < 0 || worker >= (int)p->workers.size()) return fail(FBR_EINVAL, "bad arguments");
+    CK(cudaSetDevice(p->workers[worker].device));
+    CK(cudaMalloc(dptr, bytes));
+    return FBR_OK;
+}
+
+int fbr_device_free(fbr_pool_t* p, int worker, void* dptr) {
+    if (!p || worker < 0 || worker >= (int)p->workers.size()) return fail(FBR_EINVAL, "bad arguments");
+    CK(cudaSetDevice(p->workers[worker].device));
+    CK(cudaFree(dptr));
+    return FBR_OK;
+}
+
+int fbr_memcpy_h2d(fbr_pool_t* p, int worker, void* dptr, const void* src, uint64_t bytes) {
+    if (!p || worker < 0 || worker >= (int)p->workers.size()) return fail(FBR_EINVAL, "bad arguments");
+    Worker& w = p->workers[worker];
+    CK(cudaSetDevice(w.device));
+    CK(cudaMemcpyAsync(dptr, src, bytes, cudaMemcpyHostToDevice, w.s_in));
+    CK(cudaStreamSynchronize(w.s_in));
+    return FBR_OK;
+}
+
+int fbr_memcpy_d2h(fbr_pool_t* p, int worker, void* dst, const void* dptr, uint64_t bytes) {
+    if (!p || worker < 0 || worker >= (int)p->workers.size()) return fail(FBR_EINVAL, "bad arguments");
+    Worker& w = p->workers[worker];
+    CK(cudaSetDevice(w.device));
+    CK(cudaStreamSynchronize(w.s_comp));
+    CK(cudaMemcpyAsync(dst, dptr, bytes, cudaMemcpyDeviceToHost, w.s_out));
+    CK(cudaStreamSynchronize(w.s_out));
+    return FBR_OK;
+}
+
+int fbr_payload_fill_device(fbr_pool_t* p, int worker, void* dptr, uint64_t t0, uint64_t n) {
+    if (!p || !dptr || worker < 0 || worker >= (int)p->workers.size()) return fail(FBR_EINVAL, "bad arguments");
+    std::lock_guard<std::mutex> g(p->mu);
+    Worker& w = p->workers[worker];
+    CK(cudaSetDevice(w.device));
+    const uint64_t n_vec = n * (kPayloadBytes / 16);
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((n_vec + kThreads - 1) / kThreads, (uint64_t)w.sm_count * w.occ_fill));
+    payload_fill_kernel<<<grid, kThreads, 0, w.s_comp>>>((uint4*)dptr, t0, n_vec);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(w.s_comp));
+    p->stats.fill_launches++;
+    return FBR_OK;
+}
+
+int fbr_pool_stats(fbr_pool_t* p, fbr_stats_t* s) {
+    if (!p || !s) return fail(FBR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> g(p->mu);
+    *s = p->stats;
+    return FBR_OK;
+}
+
+int fbr_pool_stats_reset(fbr_pool_t* p) {
+    if (!p) return fail(FBR_EINVAL, "NULL pool");
+    std::lock_guard<std::mutex> g(p->mu);
+    memset(&p->stats, 0, sizeof p->stats);
+    return FBR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,422 @@
+// kernels.cuh -- the sm_100a kernels of the Pool.map hot path.
+//
+//   dispatch_*_kernel  : persistent CTAs claim fixed-layout task records from the device task ring
+//                        by atomic ticket, run the mapped body, and write the unit's results plus a
+//                        16 B header into the paired slot of the result ring.
+//                        Replaces _handle_tasks + PUSH/PULL + zpool_worker_core
+//                        (fiber/pool.py:952-963, 783-824).
+//   gather_ordered_kernel : result ring -> ordered output by index placement, optional sum
+//                        epilogue.  Replaces result_conn.send xN + _res_get + Inventory.get
+//                        (fiber/pool.py:814-824, 968-973, 666-679).
+//   payload_fill_kernel : synthetic 4 KB records for BASELINE.json config 4.
+//
+// Everything here is HBM-bound byte/integer work (no dense contraction => no tensor cores):
+// 16 B vector accesses, fully coalesced, grids sized as (SM count x resident CTAs).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "bodies.cuh"
+
+namespace fbr {
+
+constexpr int kThreads = 256;
+
+// One claim unit = `count` consecutive tasks of one map.  32 B, written by the host into the
+// pinned task ring and copied to the device ring with cudaMemcpyAsync.  It is the fixed-layout
+// stand-in for the reference's pickled task tuple (seq, batch_start, func, chunk, starmap)
+// (fiber/pool.py:1181).
+struct TaskRecord {
+    uint32_t seq;       // map id (Inventory seq, fiber/pool.py:659-664), low 32 bits
+    uint32_t count;     // tasks in this unit
+    uint64_t first;     // index of the unit's first task inside the map (the reference's `batch`)
+    uint64_t arg_off;   // byte offset of the unit's first argument record in the wave's arg ring
+    uint32_t func_id;
+    uint32_t attempt;   // re-dispatch count (resilient pool)
+};
+static_assert(sizeof(TaskRecord) == 32, "task record layout is part of the ABI");
+
+// Header of a result-ring slot: the fixed-layout stand-in for the reference's per-item result
+// message (seq, batch, batch + i, res) (fiber/pool.py:814,821), one per unit instead of per item.
+struct SlotHeader {
+    uint32_t seq;
+    uint32_t count;     // bit 31: unit lost (its worker "died"), must be re-dispatched
+    uint64_t first;
+};
+static_assert(sizeof(SlotHeader) == 16, "slot header layout is part of the ABI");
+constexpr uint32_t kUnitLost = 0x80000000u;
+
+struct WaveParams {
+    const TaskRecord* records;  // device task ring window of this wave
+    SlotHeader* headers;        // result ring headers (paired with records by ticket)
+    uint8_t* ring;              // result ring payload arena
+    uint32_t* ticket;           // device counter, zero at launch
+    uint32_t n_units;
+    uint32_t slot_stride;       // bytes, multiple of 16
+    const uint8_t* args;        // device argument ring window (arg_off is relative to it)
+    uint32_t arg_stride;        // 0 => implicit index arguments
+    int64_t index_start, index_step;
+    uint64_t index_base;        // global index of the map's task 0
+    const uint8_t* shared;      // broadcast argument block
+    uint64_t shared_bytes;
+    unsigned long long* err_word;
+};
+
+// ------------------------------------------------------------------------------------------------
+// streaming 16 B accesses
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ld_stream(const void* p) { return __ldcs(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void st_vec(void* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
+
+// Ticket claim with prefetch: thread 0 holds the next ticket while the CTA works on the current
+// one, so the ~700-cycle L2 atomic round trip is off the critical path.
+struct TicketClaimer {
+    uint32_t* counter;
+    uint32_t next;  // valid in thread 0 only
+    __device__ __forceinline__ void prime() {
+        if (threadIdx.x == 0) next = atomicAdd(counter, 1u);
+    }
+    // returns the ticket for this iteration (uniform across the CTA) and prefetches the following one
+    __device__ __forceinline__ uint32_t claim(uint32_t* s_slot) {
+        __syncthreads();  // previous iteration's readers of *s_slot are done
+        if (threadIdx.x == 0) {
+            *s_slot = next;
+            next = atomicAdd(counter, 1u);
+        }
+        __syncthreads();
+        return *s_slot;
+    }
+};
+
+// ================================================================================================
+// dispatch: ThreadBody -- one thread per task, V = 16/sizeof(Res) consecutive tasks per thread so
+// each thread emits one 16 B store; a warp writes 512 contiguous bytes of the ring slot.
+// ================================================================================================
+template <class B>
+__global__ void __launch_bounds__(kThreads) dispatch_thread_kernel(const WaveParams wp) {
+    using Arg = typename B::Arg;
+    using Res = typename B::Res;
+    constexpr int V = (sizeof(Res) >= 16) ? 1 : (16 / (int)sizeof(Res));
+    __shared__ uint32_t s_ticket;
+    __shared__ int s_fault;
+    const ErrSink es{wp.err_word, &s_fault};
+
+    TicketClaimer tc{wp.ticket, 0u};
+    tc.prime();
+    for (;;) {
+        if (threadIdx.x == 0) s_fault = 0;
+        const uint32_t t = tc.claim(&s_ticket);
+        if (t >= wp.n_units) break;
+        const TaskRecord rec = wp.records[t];
+        uint8_t* slot = wp.ring + (size_t)t * wp.slot_stride;
+        const uint8_t* uargs = wp.args + rec.arg_off;
+
+        for (uint32_t base = threadIdx.x * V; base < rec.count; base += kThreads * V) {
+            alignas(16) Res r[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const uint32_t i = base + v;
+                if (i < rec.count) {
+                    Arg a;
+                    if constexpr (B::kIndexArg) {
+                        if (wp.arg_stride == 0)
+                            a = (Arg)(wp.index_start + (int64_t)(rec.first + i) * wp.index_step);
+                        else
+                            a = *reinterpret_cast<const Arg*>(uargs + (size_t)i * wp.arg_stride);
+                    } else {
+                        a = *reinterpret_cast<const Arg*>(uargs + (size_t)i * wp.arg_stride);
+                    }
+                    r[v] = B::run(a, wp.index_base + rec.first + i, es, rec.attempt);
+                } else {
+                    r[v] = Res{};
+                }
+            }
+            Res* dst = reinterpret_cast<Res*>(slot) + base;
+            if (base + V <= rec.count) {
+                st_vec(dst, *reinterpret_cast<const uint4*>(r));
+            } else {
+                for (int v = 0; v < V && base + v < rec.count; ++v) dst[v] = r[v];
+            }
+        }
+        __syncthreads();  // s_fault final
+        if (threadIdx.x == 0)
+            wp.headers[t] = SlotHeader{rec.seq, rec.count | (s_fault ? kUnitLost : 0u), rec.first};
+    }
+}
+
+// ================================================================================================
+// dispatch: payload_map_4k -- a CTA streams its unit's 4 KB records: thread j owns the j-th 16 B
+// column of every record, 4 records in flight per thread (16 KB per CTA in flight).
+//   out[w] = in[w] * 2654435761 + t   (u32 wrap), t = global task index.
+// Algorithmic bytes per task: 4096 read + 4096 written.
+// ================================================================================================
+__global__ void __launch_bounds__(kThreads) dispatch_payload_map_kernel(const WaveParams wp) {
+    __shared__ uint32_t s_ticket;
+    TicketClaimer tc{wp.ticket, 0u};
+    tc.prime();
+    constexpr int U = 4;
+    for (;;) {
+        const uint32_t t = tc.claim(&s_ticket);
+        if (t >= wp.n_units) break;
+        const TaskRecord rec = wp.records[t];
+        const uint8_t* src = wp.args + rec.arg_off + threadIdx.x * 16;
+        uint8_t* dst = wp.ring + (size_t)t * wp.slot_stride + threadIdx.x * 16;
+        const uint32_t tbase = (uint32_t)(wp.index_base + rec.first);
+        uint32_t r = 0;
+        for (; r + U <= rec.count; r += U) {
+            uint4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) v[u] = ld_stream(src + (size_t)(r + u) * wp.arg_stride);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t tt = tbase + r + u;
+                v[u].x = v[u].x * kPayloadMul + tt;
+                v[u].y = v[u].y * kPayloadMul + tt;
+                v[u].z = v[u].z * kPayloadMul + tt;
+                v[u].w = v[u].w * kPayloadMul + tt;
+                st_vec(dst + (size_t)(r + u) * kPayloadBytes, v[u]);
+            }
+        }
+        for (; r < rec.count; ++r) {
+            uint4 v = ld_stream(src + (size_t)r * wp.arg_stride);
+            const uint32_t tt = tbase + r;
+            v.x = v.x * kPayloadMul + tt; v.y = v.y * kPayloadMul + tt;
+            v.z = v.z * kPayloadMul + tt; v.w = v.w * kPayloadMul + tt;
+            st_vec(dst + (size_t)r * kPayloadBytes, v);
+        }
+        if (threadIdx.x == 0) wp.headers[t] = SlotHeader{rec.seq, rec.count, rec.first};
+    }
+}
+
+// ================================================================================================
+// dispatch: payload_checksum_4k -- one warp per record, 8 coalesced 16 B loads per lane, shuffle
+// reduce, lane 0 stores the u32.  Algorithmic bytes per task: 4096 read + 4 written.
+// ================================================================================================
+__global__ void __launch_bounds__(kThreads) dispatch_payload_checksum_kernel(const WaveParams wp) {
+    __shared__ uint32_t s_ticket;
+    TicketClaimer tc{wp.ticket, 0u};
+    tc.prime();
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (;;) {
+        const uint32_t t = tc.claim(&s_ticket);
+        if (t >= wp.n_units) break;
+        const TaskRecord rec = wp.records[t];
+        uint32_t* dst = reinterpret_cast<uint32_t*>(wp.ring + (size_t)t * wp.slot_stride);
+        for (uint32_t r = warp; r < rec.count; r += kThreads / 32) {
+            const uint8_t* src = wp.args + rec.arg_off + (size_t)r * wp.arg_stride + lane * 16;
+            uint4 v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = ld_stream(src + k * 512);
+            uint32_t s = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s += v[k].x + v[k].y + v[k].z + v[k].w;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) dst[r] = s;
+        }
+        if (threadIdx.x == 0) wp.headers[t] = SlotHeader{rec.seq, rec.count, rec.first};
+    }
+}
+
+// ================================================================================================
+// dispatch: parzen -- a CTA per task: every thread tests samples j, j+256, ... against the window
+// (samples are read from the broadcast block, L2-resident after the first task), block-reduce the
+// count, thread 0 emits (h, (k/n)/h**power).  Algorithmic bytes per task: n*dims*sizeof(T) read
+// (from L2), 16 written.
+// ================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(kThreads) dispatch_parzen_kernel(const WaveParams wp) {
+    __shared__ uint32_t s_ticket;
+    __shared__ uint32_t s_warp[kThreads / 32];
+    TicketClaimer tc{wp.ticket, 0u};
+    tc.prime();
+    const ParzenShared sh = *reinterpret_cast<const ParzenShared*>(wp.shared);
+    const T* samples = reinterpret_cast<const T*>(wp.shared + sizeof(ParzenShared));
+    for (;;) {
+        const uint32_t t = tc.claim(&s_ticket);
+        if (t >= wp.n_units) break;
+        const TaskRecord rec = wp.records[t];
+        double* dst = reinterpret_cast<double*>(wp.ring + (size_t)t * wp.slot_stride);
+        for (uint32_t i = 0; i < rec.count; ++i) {
+            const double h = *reinterpret_cast<const double*>(wp.args + rec.arg_off + (size_t)i * wp.arg_stride);
+            const T hT = (T)h;
+            uint32_t k = 0;
+            if (sh.dims == 2) {
+                for (uint32_t j = threadIdx.x; j < sh.n_samples; j += kThreads) {
+                    T row[2];
+                    if constexpr (sizeof(T) == 4) {
+                        const float2 v = reinterpret_cast<const float2*>(samples)[j];
+                        row[0] = v.x; row[1] = v.y;
+                    } else {
+                        const double2 v = reinterpret_cast<const double2*>(samples)[j];
+                        row[0] = v.x; row[1] = v.y;
+                    }
+                    k += parzen_inside<T>(row, sh, hT) ? 1u : 0u;
+                }
+            } else {
+                for (uint32_t j = threadIdx.x; j < sh.n_samples; j += kThreads)
+                    k += parzen_inside<T>(samples + (size_t)j * sh.dims, sh, hT) ? 1u : 0u;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) k += __shfl_xor_sync(0xffffffffu, k, o);
+            if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = k;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                uint32_t kn = 0;
+                for (int w = 0; w < kThreads / 32; ++w) kn += s_warp[w];
+                // (k_n / len(x_samples)) / (h ** point_x.shape[1]), float64 like the reference
+                double hp = 1.0;
+                for (uint32_t e = 0; e < sh.power; ++e) hp = __dmul_rn(hp, h);
+                dst[2 * i] = h;
+                dst[2 * i + 1] = __ddiv_rn(__ddiv_rn((double)kn, (double)sh.n_samples), hp);
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) wp.headers[t] = SlotHeader{rec.seq, rec.count, rec.first};
+    }
+}
+
+// ================================================================================================
+// gather_ordered: the result ring of one wave is treated as a flat array of 16 B vectors;
+// consecutive threads take consecutive vectors (perfect coalescing on the read side), the slot
+// header tells where the vector lands in the ordered output (out[first*R + ...], placement by
+// index, fiber/pool.py:672).  Slots are full-size except each seq's tail unit, so both sides are
+// 16 B aligned on the fast path; the slow path copies byte-wise.  Lost units are skipped and
+// appended to the lost list for re-dispatch.  Optional epilogue folds sum(results).
+// Algorithmic bytes per task: R read + R written.
+// ================================================================================================
+struct GatherParams {
+    const SlotHeader* headers;
+    const uint8_t* ring;
+    uint32_t n_units;
+    uint32_t slot_stride;     // bytes, multiple of 16
+    uint32_t result_bytes;    // R
+    uint32_t sum_kind;        // 0 none, FBR_RES_BOOL / I64 / U32
+    uint8_t* out;             // ordered output window
+    uint64_t win_first;       // map index of out[0]
+    long long* sum;           // device accumulator (sum_kind != 0)
+    uint32_t* ticket_to_reset;  // dispatch ticket of this wave, zeroed for its next use
+    uint32_t* lost_count;     // device: number of lost units appended so far (nullable)
+    uint32_t* lost_units;     // device: wave-local unit numbers of lost units
+    uint32_t lost_capacity;
+};
+
+constexpr uint32_t kSumBool = 1, kSumI64 = 2, kSumU32 = 3;
+
+__device__ __forceinline__ SlotHeader ld_header(const SlotHeader* p) {
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+    SlotHeader h;
+    h.seq = r.x; h.count = r.y; h.first = ((uint64_t)r.w << 32) | (uint64_t)r.z;
+    return h;
+}
+
+__device__ __forceinline__ long long sum_vec(const uint4& v, uint32_t kind) {
+    if (kind == kSumBool) {
+        uint32_t a = __dp4a(v.x, 0x01010101u, 0u);
+        a = __dp4a(v.y, 0x01010101u, a);
+        a = __dp4a(v.z, 0x01010101u, a);
+        a = __dp4a(v.w, 0x01010101u, a);
+        return (long long)a;
+    } else if (kind == kSumI64) {
+        return (long long)(((unsigned long long)v.y << 32) | v.x) + (long long)(((unsigned long long)v.w << 32) | v.z);
+    } else {
+        return (long long)v.x + (long long)v.y + (long long)v.z + (long long)v.w;
+    }
+}
+
+template <bool kSum>
+__global__ void __launch_bounds__(kThreads) gather_ordered_kernel(const GatherParams gp) {
+    const uint32_t vps = gp.slot_stride >> 4;                   // vectors per slot
+    const uint64_t total = (uint64_t)gp.n_units * vps;
+    const uint64_t gsize = (uint64_t)gridDim.x * kThreads;
+    long long acc = 0;
+    constexpr int U = 4;
+
+    auto place = [&](const uint4& data, const SlotHeader& h, uint32_t within) {
+        const uint32_t cnt = h.count & ~kUnitLost;
+        const uint64_t valid = (uint64_t)cnt * gp.result_bytes;
+        const uint64_t off = (uint64_t)within << 4;
+        if ((h.count & kUnitLost) || off >= valid) return;
+        uint8_t* dst = gp.out + (h.first - gp.win_first) * gp.result_bytes + off;
+        if (off + 16 <= valid && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+            st_vec(dst, data);
+            if constexpr (kSum) acc += sum_vec(data, gp.sum_kind);
+        } else {
+            const uint32_t nb = (uint32_t)((valid - off) < 16 ? (valid - off) : 16);
+            const uint8_t* sb = reinterpret_cast<const uint8_t*>(&data);
+            for (uint32_t b = 0; b < nb; ++b) dst[b] = sb[b];
+            if constexpr (kSum) {
+                if (gp.sum_kind == kSumBool) { for (uint32_t b = 0; b < nb; ++b) acc += sb[b]; }
+                else if (gp.sum_kind == kSumI64) { for (uint32_t b = 0; b + 8 <= nb; b += 8) acc += *reinterpret_cast<const long long*>(sb + b); }
+                else { for (uint32_t b = 0; b + 4 <= nb; b += 4) acc += *reinterpret_cast<const uint32_t*>(sb + b); }
+            }
+        }
+    };
+
+    uint64_t v = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+    for (; v + (U - 1) * gsize < total; v += U * gsize) {
+        uint4 data[U];
+        SlotHeader h[U];
+        uint32_t within[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t vv = v + u * gsize;
+            const uint32_t slot = (uint32_t)(vv / vps);
+            within[u] = (uint32_t)(vv - (uint64_t)slot * vps);
+            h[u] = ld_header(gp.headers + slot);
+            data[u] = ld_stream(gp.ring + (size_t)slot * gp.slot_stride + ((size_t)within[u] << 4));
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) place(data[u], h[u], within[u]);
+    }
+    for (; v < total; v += gsize) {
+        const uint32_t slot = (uint32_t)(v / vps);
+        const uint32_t within = (uint32_t)(v - (uint64_t)slot * vps);
+        const SlotHeader h = ld_header(gp.headers + slot);
+        const uint4 data = ld_stream(gp.ring + (size_t)slot * gp.slot_stride + ((size_t)within << 4));
+        place(data, h, within);
+    }
+
+    if constexpr (kSum) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        __shared__ long long s_acc[kThreads / 32];
+        if ((threadIdx.x & 31) == 0) s_acc[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long tot = 0;
+            for (int w = 0; w < kThreads / 32; ++w) tot += s_acc[w];
+            if (tot != 0) atomicAdd(reinterpret_cast<unsigned long long*>(gp.sum), (unsigned long long)tot);
+        }
+    }
+    // housekeeping by one thread: report lost units, re-arm the wave's ticket
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (gp.ticket_to_reset) *gp.ticket_to_reset = 0u;
+    }
+    if (gp.lost_count != nullptr) {
+        for (uint64_t s = (uint64_t)blockIdx.x * kThreads + threadIdx.x; s < gp.n_units; s += gsize) {
+            if (gp.headers[s].count & kUnitLost) {
+                const uint32_t k = atomicAdd(gp.lost_count, 1u);
+                if (k < gp.lost_capacity) gp.lost_units[k] = (uint32_t)s;
+            }
+        }
+    }
+}
+
+// ================================================================================================
+// payload_fill: w[t][j] = low32(splitmix64(SEED ^ (t*1024 + j))); each thread emits 16 B.
+// ================================================================================================
+__global__ void __launch_bounds__(kThreads) payload_fill_kernel(uint4* out, uint64_t t0, uint64_t n_vec) {
+    const uint64_t gsize = (uint64_t)gridDim.x * kThreads;
+    for (uint64_t v = (uint64_t)blockIdx.x * kThreads + threadIdx.x; v < n_vec; v += gsize) {
+        const uint64_t w0 = t0 * kPayloadWords + v * 4;
+        uint4 r;
+        r.x = (uint32_t)splitmix64(kPayloadSeed ^ (w0 + 0));
+        r.y = (uint32_t)splitmix64(kPayloadSeed ^ (w0 + 1));
+        r.z = (uint32_t)splitmix64(kPayloadSeed ^ (w0 + 2));
+        r.w = (uint32_t)splitmix64(kPayloadSeed ^ (w0 + 3));
+        out[v] = r;
+    }
+}
+
+}  // namespace fbr

@@ -1,0 +1,426 @@
+"""``fiber_b200.Pool`` -- the reference's ``ZPool`` / ``ResilientZPool`` surface
+(fiber/pool.py:881-1422, 1425-1688) on the B200 engine.
+
+Same constructor, method names, defaults and exceptions as the reference:
+
+* ``Pool(processes=None, initializer=None, initargs=(), maxtasksperchild=None, error_handling=False)``
+  (fiber/context.py:38-45); ``processes=None`` means 1 (fiber/pool.py:894);
+* ``map / map_async / starmap / starmap_async / apply / apply_async / imap / imap_unordered /
+  close / terminate / join / start_workers / wait_until_workers_up``;
+* ``chunksize=None`` -> 32 (fiber/pool.py:1169-1170), ``imap`` default chunksize 1 (:1218);
+* ``ValueError("Pool is not running")`` once closed (:1107-1108, 1166-1167, 1284-1285);
+  ``NotImplementedError`` for ``error_callback`` (:1162-1164); ``RuntimeError`` when a function
+  with different ``__fiber_meta__`` arrives after the workers started (:1128-1133);
+* workers start lazily on the first submission (:1122-1137).
+
+What differs, by construction: a worker is a CUDA device, the mapped callable must be bound to a
+compiled-in device body (``fiber_b200.device_body``), results come back as a buffer-backed
+``ResultArray`` (list-like; ``.tolist()`` materialises the reference's list) instead of 1e8 Python
+objects, and nothing on this path executes tasks on the CPU.
+"""
+import collections.abc
+import ctypes
+import math
+import threading
+import time
+
+import numpy as np
+
+from . import _abi, registry
+
+RUN, CLOSE, TERMINATE = 0, 1, 2
+DEFAULT_CHUNKSIZE = 32
+
+
+class _Engine:
+    """Owner of one ``fbr_pool_t``.  Destroyed when the last Python reference (pool or result
+    segment) goes away, so result buffers never dangle."""
+
+    def __init__(self, n_workers, devices, ring_bytes, timing):
+        self.lib = _abi.load()
+        ids = (ctypes.c_int * n_workers)(*devices)
+        handle = ctypes.c_void_p()
+        _abi.check(self.lib.fbr_pool_create(n_workers, ids, ring_bytes, _abi.FBR_POOL_TIMING if timing else 0,
+                                            ctypes.byref(handle)))
+        self.handle = handle
+        self.n_workers = n_workers
+        self.devices = list(devices)
+        self.lock = threading.Lock()
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            self.lib.fbr_pool_destroy(h)
+
+
+class _Segment:
+    """Pinned result segment of one map: exposes ``__array_interface__`` so NumPy views keep it (and
+    through it the engine) alive; releasing it returns the segment to the pool's pinned ring
+    (``self._inventory[job_seq] = None``, fiber/pool.py:677-679)."""
+
+    def __init__(self, engine, seq, ptr, nbytes):
+        self.engine, self.seq, self.ptr, self.nbytes = engine, seq, ptr, nbytes
+        self.__array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr or 0, False), "version": 3}
+
+    def __del__(self):
+        eng = getattr(self, "engine", None)
+        if eng is not None and eng.handle:
+            eng.lib.fbr_result_release(eng.handle, self.seq)
+
+
+class ResultArray(collections.abc.Sequence):
+    """Ordered results of one map, backed by the pinned result segment (no per-item Python
+    objects).  Behaves like the list the reference returns: indexing, slicing, iteration, ``len``,
+    ``==`` against lists; ``tolist()`` materialises it; ``sum()`` returns the device-side sum folded
+    by ``gather_ordered`` when available."""
+
+    def __init__(self, spec, array, device_sum=None):
+        self._spec = spec
+        self._a = array
+        self._sum = device_sum
+
+    def __len__(self):
+        return len(self._a)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return self._spec.rows_to_list(self._a[i])
+        return self._spec.to_python(self._a[i])
+
+    def __iter__(self):
+        step = 1 << 16
+        for s in range(0, len(self._a), step):
+            yield from self._spec.rows_to_list(self._a[s:s + step])
+
+    def __eq__(self, other):
+        if isinstance(other, ResultArray):
+            return np.array_equal(self._a, other._a)
+        if isinstance(other, (list, tuple)):
+            return len(other) == len(self) and self.tolist() == list(other)
+        return NotImplemented
+
+    def __repr__(self):
+        n = len(self)
+        head = self[:6]
+        return "ResultArray(%s%s, len=%d, body=%s)" % (head, "..." if n > 6 else "", n, self._spec.name)
+
+    def __array__(self, dtype=None, copy=None):
+        a = self._a
+        return a.astype(dtype) if dtype is not None else a
+
+    @property
+    def array(self):
+        """Zero-copy NumPy view of the pinned result segment."""
+        return self._a
+
+    def tolist(self):
+        return self._spec.rows_to_list(self._a)
+
+    def sum(self):
+        if self._sum is not None:
+            return self._sum
+        return int(self._a.sum())
+
+    def sort(self):
+        raise TypeError("ResultArray is read-only; use sorted(result) or result.tolist()")
+
+
+class MapResult:
+    """Handle of an asynchronous map (fiber/pool.py:731-743)."""
+
+    def __init__(self, pool, engine, spec, seq, n, keepalive):
+        self._pool, self._engine, self._spec, self._seq, self._n = pool, engine, spec, seq, n
+        self._keepalive = keepalive   # argument buffers must outlive the asynchronous H2D copies
+        self._result = None
+        self._segment = None
+        self._yielded = False
+
+    # -- internal ----------------------------------------------------------------------------
+    def _wait(self, timeout=None):
+        if self._result is not None:
+            return self._result
+        if self._n == 0:
+            self._result = ResultArray(self._spec, np.empty((0,) + self._spec.result_dtype()[1], self._spec.result_dtype()[0]), 0)
+            return self._result
+        res = _abi.Result()
+        eng = self._engine
+        tmo = -1 if timeout is None else int(timeout * 1000)
+        rc = eng.lib.fbr_result_wait(eng.handle, self._seq, tmo, ctypes.byref(res))
+        if rc == _abi.FBR_ETIMEOUT:
+            raise TimeoutError("map %d not finished" % self._seq)
+        if rc == _abi.FBR_ETASK:
+            self._segment = _Segment(eng, self._seq, res.data, 0)  # release on GC
+            self._raise_task_error(res)
+        _abi.check(rc)
+        self._keepalive = None
+        self._pool.recv_tasks += self._n
+        dtype, sub = self._spec.result_dtype()
+        seg = _Segment(eng, self._seq, res.data, res.n_tasks * res.result_bytes)
+        arr = np.asarray(seg).view(dtype).reshape((res.n_tasks,) + sub)
+        self._segment = seg
+        dsum = int(res.sum) if (self._flags & _abi.FBR_WANT_SUM) else None
+        self._result = ResultArray(self._spec, arr, dsum)
+        self.n_waves = res.n_waves
+        return self._result
+
+    def _raise_task_error(self, res):
+        code, task = res.err_code, res.err_task
+        name = self._spec.name
+        if code == _abi.FBR_TASK_OVERFLOW:
+            raise OverflowError("%s: result of task %d does not fit int64 (Python ints are unbounded; "
+                                "the device body refuses to wrap)" % (name, task))
+        if code == _abi.FBR_TASK_BADARG:
+            raise ValueError("%s: bad argument in task %d" % (name, task))
+        raise RuntimeError("%s: task %d failed with device error code %d" % (name, task, code))
+
+    # -- reference surface -------------------------------------------------------------------
+    def get(self, timeout=None):
+        return self._wait(timeout)
+
+    def _iter_ready(self):
+        """Yield results as ordered prefixes become final (per-wave completion events)."""
+        if self._n == 0:
+            return
+        eng = self._engine
+        done = ctypes.c_uint64(0)
+        emitted = 0
+        dtype, sub = self._spec.result_dtype()
+        # peek at the segment: results land in it wave by wave
+        while emitted < self._n:
+            _abi.check(eng.lib.fbr_result_poll(eng.handle, self._seq, ctypes.byref(done)))
+            if done.value >= self._n:
+                break
+            if done.value > emitted:
+                # an ordered prefix is final but the map is not: hand it out from the live segment
+                part = self._peek(emitted, done.value, dtype, sub)
+                yield from self._spec.rows_to_list(part)
+                emitted = done.value
+            else:
+                time.sleep(0.0002)
+        res = self._wait()
+        if emitted < self._n:
+            yield from self._spec.rows_to_list(res.array[emitted:])
+
+    def _peek(self, lo, hi, dtype, sub):
+        base = self._pool._segment_ptr(self._seq)
+        rb = self._spec.result_bytes
+        buf = (ctypes.c_char * ((hi - lo) * rb)).from_address(base + lo * rb)
+        return np.frombuffer(buf, dtype=dtype).reshape((hi - lo,) + sub).copy()
+
+    def iget_ordered(self):
+        return self._iter_ready()
+
+    def iget_unordered(self):
+        # arrival order == ring order; ordered prefixes are a valid "unordered" stream
+        return self._iter_ready()
+
+
+class ApplyResult(MapResult):
+    """fiber/pool.py:746-757: ``get()`` returns the single element."""
+
+    def get(self, timeout=None):
+        return self._wait(timeout)[0]
+
+
+class Pool:
+    """B200-native drop-in for ``fiber.Pool`` on the map/starmap/apply path."""
+
+    def __init__(self, processes=None, initializer=None, initargs=(), maxtasksperchild=None,
+                 error_handling=False, *, devices=None, ring_bytes=0, timing=False):
+        self._processes = processes if processes is not None else 1   # fiber/pool.py:894
+        if self._processes < 1:
+            raise ValueError("Number of processes must be at least 1")
+        if initializer is not None:
+            # the reference runs initializer(*initargs) inside every worker process
+            # (fiber/pool.py:858-859); a host callable cannot run inside a GPU worker.
+            raise NotImplementedError("fiber_b200.Pool: Python initializers cannot run on GPU workers")
+        self._initializer, self._initargs = initializer, initargs
+        self._maxtasksperchild = maxtasksperchild
+        self._error_handling = bool(error_handling)
+        self._devices = list(devices) if devices is not None else None
+        self._ring_bytes = int(ring_bytes)
+        self._timing = bool(timing)
+        self._state = RUN
+        self._engine = None
+        self._worker_handler_started = False
+        self._meta = None
+        self._live = {}         # seq -> data pointer of the engine-owned segment (for imap peeks)
+        self._shared_cache = collections.OrderedDict()
+        self.sent_tasks = 0     # fiber/pool.py:902-903
+        self.recv_tasks = 0
+
+    def __repr__(self):
+        return "<{}({}, {})>".format(type(self).__name__, self._processes,
+                                     self._engine.devices if self._engine else None)
+
+    # -- workers (fiber/pool.py:1118-1137, 1405-1422) ---------------------------------------------
+    def start_workers(self):
+        if self._engine is None:
+            lib = _abi.load()
+            n = ctypes.c_int(0)
+            _abi.check(lib.fbr_device_count(ctypes.byref(n)))
+            if self._devices is not None:
+                devs = self._devices
+            else:
+                # one worker per GPU; more requested processes than GPUs fold onto the GPUs we have
+                devs = list(range(min(self._processes, n.value)))
+            self._engine = _Engine(len(devs), devs, self._ring_bytes, self._timing)
+        self._worker_handler_started = True
+
+    def lazy_start_workers(self, func):
+        meta = getattr(func, "__fiber_meta__", None)
+        if meta is not None and meta != self._meta:
+            if self._worker_handler_started and self._meta is not None:
+                raise RuntimeError(
+                    "Cannot run function that has different resource "
+                    "requirements acceptable by this pool. Try creating a "
+                    "different pool for it.")
+            self._meta = meta
+        if not self._worker_handler_started:
+            self.start_workers()
+
+    def wait_until_workers_up(self):
+        self.start_workers()
+
+    @property
+    def n_workers(self):
+        self.start_workers()
+        return self._engine.n_workers
+
+    # -- submission ----------------------------------------------------------------------------------
+    def _check_running(self):
+        if self._state != RUN:
+            raise ValueError("Pool is not running")
+
+    def _shared_handle(self, blob):
+        key = registry.fingerprint(blob)
+        hit = self._shared_cache.get(key)
+        if hit is not None:
+            self._shared_cache.move_to_end(key)
+            return hit
+        eng = self._engine
+        buf = np.frombuffer(blob, dtype=np.uint8)
+        h = ctypes.c_uint64(0)
+        _abi.check(eng.lib.fbr_shared_put(eng.handle, buf.ctypes.data, buf.nbytes, ctypes.byref(h)))
+        self._shared_cache[key] = h.value
+        while len(self._shared_cache) > 8:
+            _, old = self._shared_cache.popitem(last=False)
+            eng.lib.fbr_shared_drop(eng.handle, old)
+        return h.value
+
+    def _submit(self, func, enc, kind, chunksize, cls=MapResult, want_sum=True, extra_flags=0):
+        spec = registry.spec(registry.body_name_of(func))
+        eng = self._engine
+        d = _abi.MapDesc()
+        d.func_id = spec.func_id
+        flags = kind | extra_flags
+        if want_sum and (spec.flags & _abi.FBR_BODY_SUMMABLE):
+            flags |= _abi.FBR_WANT_SUM
+        d.n_tasks = enc.n
+        d.chunksize = chunksize
+        d.arg_stride = enc.arg_stride
+        keep = [enc.args]
+        if enc.args is not None and enc.n:
+            d.args = enc.args.ctypes.data
+        d.index_start, d.index_step = enc.index_start, enc.index_step
+        if enc.shared is not None:
+            d.shared = self._shared_handle(enc.shared)
+            d.shared_bytes = len(enc.shared)
+            flags |= _abi.FBR_SHARED_HANDLE
+        d.task_index_base = enc.task_index_base
+        d.flags = flags
+        seq = ctypes.c_uint64(0)
+        if enc.n:
+            _abi.check(eng.lib.fbr_map_submit(eng.handle, ctypes.byref(d), ctypes.byref(seq)))
+        self.sent_tasks += enc.n
+        r = cls(self, eng, spec, seq.value, enc.n, keep)
+        r._flags = flags
+        return r
+
+    def _segment_ptr(self, seq):
+        # results are written into the engine-owned pinned segment wave by wave
+        eng = self._engine
+        ptr = ctypes.c_void_p()
+        _abi.check(eng.lib.fbr_result_data(eng.handle, seq, ctypes.byref(ptr)))
+        return ptr.value
+
+    @staticmethod
+    def _spec_of(func):
+        return registry.spec(registry.body_name_of(func))
+
+    def map_async(self, func, iterable, chunksize=None, callback=None, error_callback=None):
+        if error_callback:
+            raise NotImplementedError
+        self._check_running()
+        if chunksize is None:
+            chunksize = DEFAULT_CHUNKSIZE
+        if not hasattr(iterable, "__len__"):
+            iterable = list(iterable)
+        spec = self._spec_of(func)
+        self.lazy_start_workers(func)
+        return self._submit(func, spec.encode_map(iterable), _abi.FBR_MAP, chunksize)
+
+    def map(self, func, iterable, chunksize=None):
+        return self.map_async(func, iterable, chunksize).get()
+
+    def starmap_async(self, func, iterable, chunksize=None, callback=None, error_callback=None):
+        self._check_running()
+        if chunksize is None:
+            chunksize = DEFAULT_CHUNKSIZE
+        if not hasattr(iterable, "__len__"):
+            iterable = list(iterable)
+        spec = self._spec_of(func)
+        self.lazy_start_workers(func)
+        return self._submit(func, spec.encode_starmap(iterable), _abi.FBR_STARMAP, chunksize)
+
+    def starmap(self, func, iterable, chunksize=None):
+        return self.starmap_async(func, iterable, chunksize).get()
+
+    def apply_async(self, func, args=(), kwds={}, callback=None, error_callback=None):
+        self._check_running()
+        spec = self._spec_of(func)
+        self.lazy_start_workers(func)
+        return self._submit(func, spec.encode_apply(args, kwds), _abi.FBR_APPLY, 1, cls=ApplyResult, want_sum=False)
+
+    def apply(self, func, args=(), kwds={}):
+        return self.apply_async(func, args, kwds).get()
+
+    def imap(self, func, iterable, chunksize=1):
+        return self.map_async(func, iterable, chunksize).iget_ordered()
+
+    def imap_unordered(self, func, iterable, chunksize=1):
+        return self.map_async(func, iterable, chunksize).iget_unordered()
+
+    # -- shutdown (fiber/pool.py:1332-1403) -----------------------------------------------------------
+    def close(self):
+        if self._state == RUN:
+            self._state = CLOSE
+            if self._engine is not None:
+                self._engine.lib.fbr_pool_close(self._engine.handle)
+
+    def terminate(self):
+        self._state = TERMINATE
+        if self._engine is not None:
+            self._engine.lib.fbr_pool_terminate(self._engine.handle)
+
+    def join(self):
+        assert self._state in (TERMINATE, CLOSE)
+        if self._engine is not None:
+            _abi.check(self._engine.lib.fbr_pool_join(self._engine.handle))
+
+    # -- extras ------------------------------------------------------------------------------------------
+    def stats(self):
+        """``fbr_pool_stats`` as a dict (extends the reference's sent_tasks/recv_tasks counters)."""
+        self.start_workers()
+        s = _abi.Stats()
+        _abi.check(self._engine.lib.fbr_pool_stats(self._engine.handle, ctypes.byref(s)))
+        return s.as_dict()
+
+    def reset_stats(self):
+        self.start_workers()
+        _abi.check(self._engine.lib.fbr_pool_stats_reset(self._engine.handle))
+
+
+def n_jobs(processes, cpu_per_job=1):
+    """Number of job-backed workers the reference would start (fiber/pool.py:1405-1408)."""
+    return math.ceil(float(processes) / cpu_per_job)

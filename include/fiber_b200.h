@@ -1,0 +1,201 @@
+/* fiber_b200.h -- C ABI of the B200-native Pool.map engine (libfiber_b200.so).
+ *
+ * This is the drop-in boundary for the ONE hot path of uber/fiber this repository replaces:
+ * Pool.map / starmap / apply_async task scatter + result gather.  The reference is pure Python
+ * and has no FFI of its own; each entry point below therefore cites the reference *interface* it
+ * stands in for (paths relative to the reference checkout, fiber @ ad6faf02).  A reference
+ * maintainer binds them with ctypes exactly as fiber_b200/_abi.py does.
+ *
+ * Conventions: plain pointers and sizes only (no torch / C++ types); every function returns
+ * FBR_OK (0) or a negative fbr_status; fbr_last_error() gives the thread-local message.  Blocking
+ * calls (fbr_result_wait, fbr_pool_join) do not touch Python and are called with the GIL released.
+ * The library never computes a task on the CPU: without a usable CUDA device fbr_pool_create
+ * fails with FBR_ENODEV.
+ */
+#ifndef FIBER_B200_H_
+#define FIBER_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FBR_ABI_VERSION 1
+
+typedef enum fbr_status {
+    FBR_OK = 0,
+    FBR_EINVAL = -1,    /* bad argument */
+    FBR_ECUDA = -2,     /* CUDA runtime error (message has the cudaError string) */
+    FBR_ENOMEM = -3,
+    FBR_ESTATE = -4,    /* pool not in RUN state: the ABI face of ValueError("Pool is not running"),
+                           fiber/pool.py:1107-1108,1166-1167,1284-1285 */
+    FBR_ETIMEOUT = -5,
+    FBR_ETASK = -6,     /* a device body reported a task error (see fbr_result_t.err_*) */
+    FBR_ENODEV = -7,    /* no CUDA device: there is no CPU fallback */
+    FBR_ENOENT = -8     /* unknown body name / seq */
+} fbr_status;
+
+typedef struct fbr_pool fbr_pool_t;
+
+/* ---- library ------------------------------------------------------------------------------ */
+int fbr_abi_version(void);
+const char* fbr_last_error(void);
+/* fiber/context.py:61-62 cpu_count(): the engine's unit of parallel hardware is the GPU. */
+int fbr_device_count(int* n);
+
+/* ---- device-body registry -------------------------------------------------------------------
+ * The reference ships `func` to workers by pickle reference (fiber/pool.py:961) and calls it at
+ * fiber/pool.py:806,809,820.  A Python callable cannot run on a GPU, so callables are bound to a
+ * compiled-in device body by name; unbound callables are rejected by the host layer. */
+typedef enum fbr_result_kind {
+    FBR_RES_BYTES = 0,   /* opaque fixed-size record */
+    FBR_RES_BOOL = 1,    /* uint8 0/1  (Python bool) */
+    FBR_RES_I64 = 2,     /* int64      (Python int) */
+    FBR_RES_U32 = 3,     /* uint32     (Python int) */
+    FBR_RES_F64X2 = 4,   /* two float64 (Python tuple of floats) */
+    FBR_RES_NONE = 5     /* body returns None; one pad byte per task */
+} fbr_result_kind;
+
+#define FBR_BODY_INDEX_ARG 0x1u   /* body can take the task index itself as its int64 argument */
+#define FBR_BODY_NEEDS_SHARED 0x2u /* body reads a shared (broadcast) argument block */
+#define FBR_BODY_SUMMABLE 0x4u    /* gather_ordered can fold sum(results) (bool/int64/u32) */
+
+typedef struct fbr_body_info {
+    int32_t func_id;
+    uint32_t arg_bytes;      /* fixed-layout per-task argument record */
+    uint32_t result_bytes;   /* fixed-layout per-task result record */
+    uint32_t result_kind;    /* fbr_result_kind */
+    uint32_t flags;          /* FBR_BODY_* */
+    uint32_t unit_tasks;     /* preferred claim-unit size (tasks per ring slot) */
+    char name[40];
+} fbr_body_info_t;
+
+int fbr_body_count(int* n);
+int fbr_body_info(int func_id, fbr_body_info_t* info);
+int fbr_body_lookup(const char* name, int* func_id);
+
+/* ---- pool lifecycle -------------------------------------------------------------------------
+ * fbr_pool_create   <- ZPool.__init__ (fiber/pool.py:888-943) + worker start
+ *                      (_maintain_workers, fiber/pool.py:1009-1057) + local_backend.create_job
+ *                      (fiber/local_backend.py:37-42): one worker == one CUDA device with its
+ *                      three streams and its ring set, instead of one subprocess with two sockets.
+ * fbr_pool_close    <- ZPool.close      (fiber/pool.py:1337-1353)
+ * fbr_pool_terminate<- ZPool.terminate  (fiber/pool.py:1355-1388)
+ * fbr_pool_join     <- ZPool.join       (fiber/pool.py:1390-1403); requires close/terminate first
+ * fbr_pool_destroy  frees everything (the reference relies on process exit).
+ * ring_bytes: size of each device ring arena per worker (result ring, and each half of the
+ * argument / ordered-output staging rings); 0 selects the default (256 MiB). */
+#define FBR_POOL_TIMING 0x1u  /* bracket every dispatch/gather launch with CUDA events (stats) */
+int fbr_pool_create(int n_workers, const int* device_ids, uint64_t ring_bytes, uint32_t flags,
+                    fbr_pool_t** pool);
+int fbr_pool_close(fbr_pool_t* pool);
+int fbr_pool_terminate(fbr_pool_t* pool);
+int fbr_pool_join(fbr_pool_t* pool);
+int fbr_pool_destroy(fbr_pool_t* pool);
+int fbr_pool_n_workers(fbr_pool_t* pool, int* n);
+int fbr_pool_worker_device(fbr_pool_t* pool, int worker, int* device_id);
+
+/* ---- map submission -------------------------------------------------------------------------
+ * fbr_map_submit <- ZPool.map_async / starmap_async / apply_async (fiber/pool.py:1139-1184,
+ * 1258-1305, 1089-1116) + _handle_tasks (fiber/pool.py:952-963): cut [0,n_tasks) into chunks,
+ * write one fixed-layout task record per claim unit into the pinned task ring, cudaMemcpyAsync
+ * them (and the argument records) to the worker's device ring, launch the persistent-CTA
+ * dispatch kernel and the ordered gather.  Returns immediately with the map's `seq`
+ * (Inventory.add, fiber/pool.py:659-664). */
+#define FBR_MAP 0x0u            /* 5th task-tuple field False (fiber/pool.py:1181) */
+#define FBR_STARMAP 0x1u        /* 5th field True, item = (args,)      (fiber/pool.py:1297-1301) */
+#define FBR_APPLY 0x2u          /* 5th field True, item = (args, kwds) (fiber/pool.py:1112-1113) */
+#define FBR_KIND_MASK 0x3u
+#define FBR_ARGS_DEVICE 0x10u   /* args/shared are device pointers on worker 0 (n_workers must be 1) */
+#define FBR_OUT_DEVICE 0x20u    /* out is a device pointer on worker 0 (n_workers must be 1) */
+#define FBR_WANT_SUM 0x40u      /* fold sum(results) into fbr_result_t.sum (FBR_BODY_SUMMABLE) */
+#define FBR_SHUFFLE 0x80u       /* permute task records inside each wave (arrival != index order;
+                                   exercises placement-by-index, fiber/pool.py:672) */
+#define FBR_FULL_WINDOW 0x100u  /* keep the whole ordered output resident on the device until the
+                                   map completes (needed when units may be re-dispatched) */
+#define FBR_SHARED_HANDLE 0x200u /* `shared` is a handle from fbr_shared_put, not a pointer */
+
+typedef struct fbr_map_desc {
+    int32_t func_id;
+    uint32_t flags;
+    uint64_t n_tasks;
+    uint32_t chunksize;      /* 0 -> 32 (fiber/pool.py:1169-1170) */
+    uint32_t arg_stride;     /* bytes between argument records; 0 -> implicit index arguments */
+    const void* args;        /* n_tasks records of arg_stride bytes (host, ideally pinned; or device) */
+    int64_t index_start;     /* implicit argument of task i = index_start + i*index_step (range()) */
+    int64_t index_step;
+    const void* shared;      /* broadcast argument block (e.g. parzen samples), may be NULL */
+    uint64_t shared_bytes;
+    void* out;               /* NULL: engine-owned pinned result segment; else n_tasks*result_bytes */
+    uint64_t task_index_base;/* global index of task 0 (sharded maps: rank's block start) */
+    uint64_t shuffle_seed;
+} fbr_map_desc_t;
+
+int fbr_map_submit(fbr_pool_t* pool, const fbr_map_desc_t* desc, uint64_t* seq);
+
+/* Broadcast argument blocks (initargs / arguments every task shares, e.g. the parzen sample array
+ * the reference pickles into each of its 102 task messages): uploaded once to every
+ * worker's device, then referenced by handle (desc.shared = (void*)handle + FBR_SHARED_HANDLE). */
+int fbr_shared_put(fbr_pool_t* pool, const void* host, uint64_t bytes, uint64_t* handle);
+int fbr_shared_drop(fbr_pool_t* pool, uint64_t handle);
+
+/* ---- result collection ----------------------------------------------------------------------
+ * fbr_result_wait    <- MapResult.get -> Inventory.get (fiber/pool.py:736-737, 666-679)
+ * fbr_result_poll    <- Inventory.iget_ordered / iget_unordered progress (fiber/pool.py:681-728)
+ * fbr_result_release <- `self._inventory[job_seq] = None` (fiber/pool.py:677-679) */
+typedef struct fbr_result {
+    uint64_t seq;
+    uint64_t n_tasks;
+    uint32_t result_bytes;
+    uint32_t result_kind;
+    void* data;              /* ordered results: pinned host (or the caller's `out`) */
+    int64_t sum;             /* valid with FBR_WANT_SUM */
+    uint32_t err_code;       /* 0, or fbr_task_error of the lowest failing task */
+    uint32_t n_waves;
+    uint64_t err_task;       /* index of that task */
+} fbr_result_t;
+
+typedef enum fbr_task_error {
+    FBR_TASK_OK = 0,
+    FBR_TASK_OVERFLOW = 1,   /* int64 result overflow (Python ints are unbounded: fail loudly) */
+    FBR_TASK_BADARG = 2,
+    FBR_TASK_FAULT = 3       /* injected fault (resilient-pool tests) */
+} fbr_task_error;
+
+int fbr_result_wait(fbr_pool_t* pool, uint64_t seq, int timeout_ms, fbr_result_t* res);
+int fbr_result_poll(fbr_pool_t* pool, uint64_t seq, uint64_t* n_done);
+/* Address of the map's ordered-result buffer without waiting: tasks [0, n_done) of it are final. */
+int fbr_result_data(fbr_pool_t* pool, uint64_t seq, void** data);
+int fbr_result_release(fbr_pool_t* pool, uint64_t seq);
+
+/* ---- memory helpers ------------------------------------------------------------------------
+ * Pinned host segments are the endpoints that replace LazyZConnection sockets
+ * (fiber/queues.py:190-249): the host encodes argument records straight into them. */
+int fbr_host_alloc(fbr_pool_t* pool, uint64_t bytes, void** ptr);
+int fbr_host_free(fbr_pool_t* pool, void* ptr);
+int fbr_device_alloc(fbr_pool_t* pool, int worker, uint64_t bytes, void** dptr);
+int fbr_device_free(fbr_pool_t* pool, int worker, void* dptr);
+int fbr_memcpy_h2d(fbr_pool_t* pool, int worker, void* dptr, const void* src, uint64_t bytes);
+int fbr_memcpy_d2h(fbr_pool_t* pool, int worker, void* dst, const void* dptr, uint64_t bytes);
+/* Fill device memory with the synthetic 4 KB payload records of tasks [t0, t0+n). */
+int fbr_payload_fill_device(fbr_pool_t* pool, int worker, void* dptr, uint64_t t0, uint64_t n);
+
+/* ---- statistics ------------------------------------------------------------------------------
+ * ZPool keeps bare counters sent_tasks/recv_tasks (fiber/pool.py:902-903); these extend them. */
+typedef struct fbr_stats {
+    uint64_t tasks_submitted, tasks_completed;
+    uint64_t units_dispatched;          /* task records claimed by persistent CTAs */
+    uint64_t dispatch_launches, gather_launches, fill_launches;
+    uint64_t h2d_bytes, d2h_bytes;
+    double dispatch_ms, gather_ms;      /* summed CUDA-event time (FBR_POOL_TIMING only) */
+    uint64_t gather_bytes;              /* algorithmic bytes moved by gather_ordered (read+write) */
+    uint64_t dispatch_bytes;            /* algorithmic bytes of the dispatch kernels (args+results) */
+} fbr_stats_t;
+int fbr_pool_stats(fbr_pool_t* pool, fbr_stats_t* stats);
+int fbr_pool_stats_reset(fbr_pool_t* pool);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FIBER_B200_H_ */

@@ -1,0 +1,341 @@
+"""GPU parity tests: fiber_b200.Pool (through the C ABI) vs the oracle / the golden vectors produced
+by the real reference pool.  Restates tests/test_pool.py of the reference with the same functions
+and values.  Bit-exact for every integer / byte result; parzen_f32 carries the stated tolerance."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import fiber_b200
+from fiber_b200 import _abi
+
+from . import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pool():
+    p = fiber_b200.Pool(4)
+    yield p
+    p.terminate()
+    p.join()
+
+
+# ---- tests/test_pool.py:86-158 ---------------------------------------------------------------------
+def test_pool_basic():
+    pool = fiber_b200.Pool(2)
+    res = pool.map(W.f, [1, 2, 3])
+    pool.terminate()
+    pool.join()
+    assert res == [1, 4, 9]
+
+
+def test_pool_more(golden):
+    pool = fiber_b200.Pool(4)
+    pool.start_workers()
+    res = pool.map(W.f, [i for i in range(1000)])
+    pool.wait_until_workers_up()
+    pool.terminate()
+    pool.join()
+    assert res == [i ** 2 for i in range(1000)]
+    assert res == golden("pool_known_answers")["map_1000"]
+
+
+def test_pool_apply(pool):
+    assert pool.apply_async(W.f, (42,)).get() == 42 * 42
+    assert pool.apply(W.f, (36,)) == 36 * 36
+    assert pool.apply(W.fy, (36,), {"y": 2}) == 36 * 36 * 2
+
+
+def test_pool_imap(pool):
+    assert list(pool.imap(W.f, [x for x in range(100)], 1)) == [x * x for x in range(100)]
+    res = list(pool.imap_unordered(W.f, [x for x in range(100)], 1))
+    assert len(res) == 100
+    res.sort()
+    assert res == [x * x for x in range(100)]
+
+
+def test_pool_starmap(pool):
+    assert pool.starmap(W.f, [(x,) for x in range(100)], 1) == [x * x for x in range(100)]
+    assert pool.starmap_async(W.f, [(x,) for x in range(100)], 1).get() == [x * x for x in range(100)]
+
+
+def test_pool_starmap2(pool):
+    assert pool.starmap(W.f2, [(x, x) for x in range(100)], 10) == [x * x for x in range(100)]
+    assert pool.starmap_async(W.f, [(x,) for x in range(100)], 10).get() == [x * x for x in range(100)]
+
+
+def test_pool_close():                                      # tests/test_pool.py:236-245
+    pool = fiber_b200.Pool(2)
+    assert pool.map(W.f, [1, 2, 3]) == [1, 4, 9]
+    pool.close()
+    with pytest.raises(ValueError):
+        pool.map(W.f, [1, 2, 3])
+    pool.join()
+
+
+def test_many_jobs():                                       # tests/test_pool.py:247-270
+    workers = 5
+    pool = fiber_b200.Pool(workers)
+    pool.start_workers()
+    pool.wait_until_workers_up()
+    res = [None] * workers
+    for i in range(1000 // workers):
+        for j in range(workers):
+            res[j] = pool.apply_async(W.sleep_worker, (0.0001,))
+        for j in range(workers):
+            assert res[j].get() is None
+    pool.terminate()
+    pool.join()
+
+
+def test_golden_known_answers(pool, golden):
+    g = golden("pool_known_answers")
+    assert pool.map(W.f, []) == g["map_empty"] == []
+    assert pool.map(W.f, list(range(-50, 51)), 7) == g["map_negative_cs7"]
+    assert pool.map(W.f, list(range(10)), 1000) == g["map_cs_larger_than_n"]
+    assert pool.map(W.f, range(5, 500, 7)) == g["map_range_step"]
+    assert pool.map(W.f, (i for i in range(33))) == g["map_generator"]
+    assert pool.map(W.f, [3037000499, -3037000499, 2 ** 31, -(2 ** 31)]) == g["map_bigint"]
+    r1 = pool.map_async(W.f, range(0, 200))
+    r2 = pool.starmap_async(W.fy, [(x,) for x in range(100)])
+    assert r2.get() == g["two_inflight_second"]
+    assert r1.get() == g["two_inflight_first"]
+    assert pool.map(W.identity, [i for i in range(300)], chunksize=1) == g["resilient_map_300_cs1"]
+    assert pool.apply(W.fy, (36,), {"y": 2}) == g["apply_kwds_36_y2"]
+
+
+def test_overflow_fails_loudly(pool):
+    with pytest.raises(OverflowError):
+        pool.map(W.f, [1, 2, 3037000500])        # 3037000500**2 > 2**63-1: Python would not wrap
+    with pytest.raises(OverflowError):
+        pool.map(W.f, [2 ** 70])
+
+
+def test_unbound_callable_is_rejected(pool):
+    with pytest.raises(TypeError):
+        pool.map(W.unbound, [1, 2, 3])
+    with pytest.raises(TypeError):
+        pool.map(print, [1, 2, 3])
+
+
+# ---- pi_estimation: bit-exact vs the reference pool's output ----------------------------------------
+def test_pi_estimation_golden(pool, golden):
+    g = golden("pi_inside_det")
+    n = g["n"]
+    res = pool.map(W.is_inside, range(0, n))
+    arr = np.asarray(res).view(np.uint8)
+    assert res[:256] == [bool(v) for v in g["head_256"]]
+    assert hashlib.sha256(arr.tobytes()).hexdigest() == g["sha256_uint8"]
+    assert res.sum() == g["count"] == int(arr.sum())            # device-side sum == host sum == reference
+    pi = 4.0 * res.sum() / n
+    assert 3 < pi < 4 and pi == g["pi"]                          # tests/test_pool.py:272-276
+    assert [int(arr[i:i + 65536].sum()) for i in range(0, n, 65536)] == g["block_65536_counts"]
+    # explicit argument records (a list, not a range) and the awkward task ids
+    assert pool.map(W.is_inside, g["special_args"]) == [bool(v) for v in g["special_results"]]
+    assert pool.map(W.is_inside, list(range(1000)), chunksize=7) == [bool(v) for v in g["head_256"]] + res[256:1000]
+
+
+def test_pi_estimation_1e8_vs_c_oracle(golden):
+    """BASELINE.json config 2 at full size against the plain-C oracle (seconds on the CPU)."""
+    from oracle import cref
+    n = 10 ** 8
+    pool = fiber_b200.Pool(1)
+    res = pool.map(W.is_inside, range(n))
+    ref, count = cref.pi_inside_range(0, n)
+    assert res.sum() == count
+    assert np.array_equal(np.asarray(res).view(np.uint8), ref)
+    # size-independent properties: a sharded / strided evaluation agrees with the monolithic one
+    part = pool.map(W.is_inside, range(12345678, 12345678 + 4096))
+    assert np.array_equal(np.asarray(part).view(np.uint8), ref[12345678:12345678 + 4096])
+    strided = pool.map(W.is_inside, range(3, n, 1000003))
+    assert np.array_equal(np.asarray(strided).view(np.uint8), ref[3::1000003])
+    pool.terminate()
+    pool.join()
+
+
+# ---- parzen: fp64 body bit-exact, fp32 body within the stated tolerance ------------------------------
+def _parzen_inputs():
+    from oracle import bodies as B
+    return B.parzen_example_inputs()
+
+
+def test_parzen_f64_bit_exact(pool, golden):
+    g = golden("parzen_102")
+    xs, px, widths = _parzen_inputs()
+    assert hashlib.sha256(np.ascontiguousarray(xs).tobytes()).hexdigest() == g["samples_sha256_f64"], \
+        "numpy RNG stream differs from the golden run; regenerate tests/golden"
+    want = [(float.fromhex(h), float.fromhex(d)) for h, d in g["results_hex"]]
+    # exactly as examples/parzen_estimation.py:22-28
+    handles = [pool.apply_async(W.parzen_estimation, args=(xs, px, w)) for w in widths]
+    results = [h.get() for h in handles]
+    results.sort()
+    assert results == want
+    # and as one starmap with chunksize 1
+    star = pool.starmap(W.parzen_estimation, [(xs, px, w) for w in widths], 1)
+    assert sorted(star) == want
+
+
+def test_parzen_f32_tolerance(pool, golden):
+    """fp32 window test (north-star): k_n may differ from fp64 only on boundary samples, i.e. those
+    with | |x_d|/h - 0.5 | <= 2^-22 * max(1, |x_d|/h); density rtol 1e-6 once k_n matches."""
+    from oracle import bodies as B, cref
+    g = golden("parzen_102")
+    xs, px, widths = _parzen_inputs()
+    star = pool.starmap(W.parzen_estimation_f32, [(xs, px, w) for w in widths], 1)
+    n = len(xs)
+    mismatches = 0
+    for (h, dens), w, k64 in zip(star, widths, g["k_n"]):
+        assert h == w
+        k_gpu = int(round(dens * h * n))
+        k32 = cref.parzen_count(xs, px, w, np.float32)          # CPU fp32 restatement
+        assert k_gpu == k32                                       # bit-exact vs same-precision oracle
+        assert abs(k_gpu - k64) <= B.parzen_boundary_count(xs, px, w)
+        mismatches += k_gpu != k64
+        if k_gpu == k64:
+            want = (k64 / n) / h
+            assert abs(dens - want) <= 1e-6 * abs(want)
+    assert mismatches <= 2
+
+
+# ---- synthetic 4 KB payload map ---------------------------------------------------------------------
+def test_payload_map_golden(pool, golden):
+    from oracle import bodies as B
+    g = golden("payload_map")
+    nt = g["n_tasks"]
+    recs = B.payload_records_np(0, nt)
+    assert hashlib.sha256(recs.tobytes()).hexdigest() == g["input_sha256_u32le"]
+    out = pool.starmap(W.payload_map, [(t, recs[t]) for t in range(nt)], 8)
+    arr = np.asarray(out)
+    assert hashlib.sha256(arr.tobytes()).hexdigest() == g["output_sha256_u32le"]
+    assert arr[:2, :8].tolist() == g["output_head"] and arr[-1, -8:].tolist() == g["output_tail"]
+    cks = pool.starmap(W.payload_checksum, [(t, recs[t]) for t in range(nt)], 8)
+    assert cks == g["checksums"]
+    assert cks.sum() == sum(g["checksums"])
+
+
+@pytest.mark.parametrize("n,chunksize", [(1, None), (31, None), (33, 5), (1000, None), (4097, 32), (20000, 1000)])
+def test_payload_map_vs_oracle(pool, n, chunksize):
+    from oracle import cref
+    recs = cref.payload_records(0, n)
+    out = pool.map(W.payload_map, recs, chunksize)
+    assert np.array_equal(np.asarray(out), cref.payload_map(0, recs))
+    cks = pool.map(W.payload_checksum, recs, chunksize)
+    assert np.array_equal(np.asarray(cks), cref.payload_checksum(recs))
+
+
+def test_payload_roundtrip_property():
+    """Size-independent property at a size the CPU oracle would take long for: the map is affine in
+    u32, so inverting it with the modular inverse of 2654435761 recovers the input."""
+    from oracle import cref
+    n = 200000                                   # 0.8 GB in, 0.8 GB out, several waves
+    pool = fiber_b200.Pool(1)
+    recs = cref.payload_records(7, n)
+    res = pool.map(W.payload_map, recs)
+    out = np.asarray(res)
+    inv = pow(2654435761, -1, 2 ** 32)
+    t = np.arange(n, dtype=np.uint64).astype(np.uint32)[:, None]
+    with np.errstate(over="ignore"):
+        back = (out - t) * np.uint32(inv)
+    assert np.array_equal(back, recs)
+    pool.terminate()
+    pool.join()
+
+
+# ---- engine behaviour: waves, placement by index, device sum, stats ----------------------------------
+def _raw_map(pool, name, n, flags=0, chunksize=0, ring=None):
+    """Submit through the C ABI directly (index arguments) and return the ordered result bytes."""
+    import ctypes
+    from fiber_b200 import registry
+    spec = registry.spec(name)
+    eng = pool._engine
+    d = _abi.MapDesc()
+    d.func_id, d.flags, d.n_tasks, d.chunksize = spec.func_id, flags, n, chunksize
+    d.index_start, d.index_step, d.shuffle_seed = 0, 1, 12345
+    seq = ctypes.c_uint64(0)
+    _abi.check(eng.lib.fbr_map_submit(eng.handle, ctypes.byref(d), ctypes.byref(seq)))
+    res = _abi.Result()
+    _abi.check(eng.lib.fbr_result_wait(eng.handle, seq.value, -1, ctypes.byref(res)))
+    buf = np.frombuffer((ctypes.c_char * (n * spec.result_bytes)).from_address(res.data), dtype=np.uint8).copy()
+    out = (buf, int(res.sum), int(res.n_waves))
+    _abi.check(eng.lib.fbr_result_release(eng.handle, seq.value))
+    return out
+
+
+def test_placement_by_index_under_shuffled_arrival():
+    """Task records are permuted inside every wave, so ring (arrival) order != index order; the
+    gather must still place every unit at its index (fiber/pool.py:672)."""
+    from oracle import cref
+    pool = fiber_b200.Pool(1, ring_bytes=1 << 20)            # 1 MiB rings -> many waves
+    pool.start_workers()
+    n = 3_000_017
+    ref, count = cref.pi_inside_range(0, n)
+    plain, s0, w0 = _raw_map(pool, "pi_inside_det", n, _abi.FBR_WANT_SUM)
+    shuf, s1, w1 = _raw_map(pool, "pi_inside_det", n, _abi.FBR_WANT_SUM | _abi.FBR_SHUFFLE)
+    full, s2, w2 = _raw_map(pool, "pi_inside_det", n, _abi.FBR_WANT_SUM | _abi.FBR_SHUFFLE | _abi.FBR_FULL_WINDOW)
+    assert w0 > 1 and w1 > 1
+    assert np.array_equal(plain, ref) and np.array_equal(shuf, ref) and np.array_equal(full, ref)
+    assert s0 == s1 == s2 == count
+    sq, ssum, _ = _raw_map(pool, "square_i64", 100003, _abi.FBR_WANT_SUM | _abi.FBR_SHUFFLE, chunksize=7)
+    want = np.arange(100003, dtype=np.int64) ** 2
+    assert np.array_equal(sq.view(np.int64), want) and ssum == int(want.sum())
+    pool.terminate()
+    pool.join()
+
+
+def test_imap_streams_across_waves():
+    pool = fiber_b200.Pool(1, ring_bytes=1 << 20)
+    n = 600_000
+    it = pool.imap(W.f, range(n))
+    first = [next(it) for _ in range(10)]
+    assert first == [i * i for i in range(10)]
+    rest = list(it)
+    assert len(rest) == n - 10 and rest[-1] == (n - 1) ** 2
+    got = sorted(pool.imap_unordered(W.identity, range(n), 64))
+    assert got == list(range(n))
+    pool.terminate()
+    pool.join()
+
+
+def test_meta_mismatch_after_start():                       # fiber/pool.py:1128-1133
+    pool = fiber_b200.Pool(1)
+
+    @fiber_b200.device_body("square_i64", gpu=2)
+    def g(x):
+        return x * x
+    assert pool.map(W.f, [2]) == [4]
+    with pytest.raises(RuntimeError):
+        pool.map(g, [2])
+    pool.terminate()
+    pool.join()
+
+
+def test_error_callback_not_implemented(pool):              # fiber/pool.py:1162-1164
+    with pytest.raises(NotImplementedError):
+        pool.map_async(W.f, [1], error_callback=lambda e: None)
+
+
+def test_stats_and_launch_counts():
+    pool = fiber_b200.Pool(1, timing=True)
+    pool.map(W.is_inside, range(10 ** 6))
+    s = pool.stats()
+    assert s["tasks_submitted"] == s["tasks_completed"] == 10 ** 6
+    assert s["dispatch_launches"] >= 1 and s["gather_launches"] >= 1
+    assert s["d2h_bytes"] >= 10 ** 6 and s["gather_bytes"] == 2 * 10 ** 6
+    assert s["dispatch_ms"] > 0 and s["gather_ms"] > 0
+    pool.terminate()
+    pool.join()
+
+
+def test_multi_worker_blocks_if_available():
+    if fiber_b200.cpu_count() < 2:
+        pytest.skip("single GPU box")
+    from oracle import cref
+    pool = fiber_b200.Pool(fiber_b200.cpu_count())
+    n = 5_000_000
+    ref, count = cref.pi_inside_range(0, n)
+    res = pool.map(W.is_inside, range(n))
+    assert res.sum() == count and np.array_equal(np.asarray(res).view(np.uint8), ref)
+    pool.terminate()
+    pool.join()
