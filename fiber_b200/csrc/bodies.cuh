@@ -48,7 +48,9 @@ struct ErrSink {
 // checked int64 arithmetic: Python ints are unbounded, so overflow must fail loudly, not wrap.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int64_t mul_i64_checked(int64_t a, int64_t b, bool& ovf) {
-    int64_t lo = a * b;  // wraps
+    // low half in unsigned arithmetic: signed overflow is UB and nvcc exploits it (it folded
+    // `a*a >> 63` to 0 for the square body, hiding every overflow)
+    int64_t lo = (int64_t)((uint64_t)a * (uint64_t)b);
     int64_t hi = __mul64hi(a, b);
     ovf |= (hi != (lo >> 63));
     return lo;

@@ -79,6 +79,8 @@ def _as_i64(values, what):
         a = np.asarray(values)
     except OverflowError as e:
         raise OverflowError("%s: Python int too large for the int64 task record" % what) from e
+    if a.size == 0:
+        return np.zeros(a.shape if a.ndim else (0,), dtype=np.int64)
     if a.dtype == object:
         raise OverflowError("%s: arguments do not fit the int64 task record (got %r...)" % (what, values[:1]))
     if a.dtype.kind not in "iub":
