@@ -362,7 +362,15 @@ static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const fbr_map_d
     if (host_args) units_cap = std::min<uint64_t>(units_cap, p->ring_bytes / ((uint64_t)unit * d.arg_stride));
     if (!full_window) units_cap = std::min<uint64_t>(units_cap, p->ring_bytes / ((uint64_t)unit * R));
     if (units_cap == 0) return fail(FBR_ENOMEM, "ring_bytes=%llu too small for one claim unit of %u tasks", (unsigned long long)p->ring_bytes, unit);
-    const uint64_t wave_tasks_cap = units_cap * unit;
+    uint64_t wave_tasks_cap = units_cap * unit;
+    // Host-resident output: cut large maps into ~8 waves (>= 8 MiB of results each) so the D2H of
+    // wave w overlaps the kernels of wave w+1 instead of trailing one monolithic launch.
+    if (!full_window || host_args) {
+        const uint64_t bytes_per_task = std::max<uint64_t>(R, host_args ? d.arg_stride : 0);
+        const uint64_t min_wave_tasks = round_up(std::max<uint64_t>(1, (8ull << 20) / bytes_per_task), unit);
+        const uint64_t eighth = round_up((part.count + 7) / 8, unit);
+        wave_tasks_cap = std::min(wave_tasks_cap, std::max(min_wave_tasks, eighth));
+    }
 
     // staging
     if (host_args)
