@@ -1,0 +1,190 @@
+"""CPU: the C-ABI library loads, exports exactly what include/fiber_b200.h declares, describes its
+device bodies, and refuses to run without a GPU (no CPU fallback).  Plus the host-side logic that
+needs no device: record encoders, the callable registry, Pool argument validation."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import fiber_b200
+from fiber_b200 import _abi, registry
+
+from . import workloads as W
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _gpu_present():
+    n = ctypes.c_int(0)
+    return _abi.load().fbr_device_count(ctypes.byref(n)) == 0 and n.value > 0
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "fiber_b200.h")).read()
+    declared = sorted(set(re.findall(r"^(?:int|const char\*)\s+(fbr_\w+)\s*\(", header, flags=re.M)))
+    assert declared == sorted(_abi.SYMBOLS), set(declared) ^ set(_abi.SYMBOLS)
+    lib = ctypes.CDLL(_abi.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _abi.load().fbr_abi_version() == _abi.FBR_ABI_VERSION == int(re.search(r"#define FBR_ABI_VERSION (\d+)", header).group(1))
+
+
+def test_header_constants_match_binding():
+    header = open(os.path.join(ROOT, "include", "fiber_b200.h")).read()
+    for name in ("FBR_STARMAP", "FBR_APPLY", "FBR_ARGS_DEVICE", "FBR_OUT_DEVICE", "FBR_WANT_SUM", "FBR_SHUFFLE",
+                 "FBR_FULL_WINDOW", "FBR_SHARED_HANDLE", "FBR_POOL_TIMING", "FBR_BODY_INDEX_ARG", "FBR_BODY_SUMMABLE"):
+        m = re.search(r"#define %s (0x[0-9a-fA-F]+)u" % name, header)
+        assert m and int(m.group(1), 16) == getattr(_abi, name), name
+    for name in ("FBR_EINVAL", "FBR_ESTATE", "FBR_ETASK", "FBR_ENODEV", "FBR_ENOENT"):
+        m = re.search(r"%s = (-\d+)" % name, header)
+        assert m and int(m.group(1)) == getattr(_abi, name), name
+    # struct sizes the C side static_asserts / the binding mirrors
+    assert ctypes.sizeof(_abi.MapDesc) == 88 and ctypes.sizeof(_abi.Result) == 56 and ctypes.sizeof(_abi.BodyInfo) == 64
+
+
+def test_body_table():
+    names = fiber_b200.body_names()
+    assert set(names) >= {"square_i64", "mul2_i64", "square_scale_i64", "identity_i64", "pi_inside_det", "parzen_f32",
+                          "parzen_f64", "payload_map_4k", "payload_checksum_4k", "sleep_f64", "fault_identity_i64"}
+    s = registry.spec("pi_inside_det")
+    assert (s.arg_bytes, s.result_bytes, s.result_kind) == (8, 1, _abi.FBR_RES_BOOL)
+    assert s.flags & _abi.FBR_BODY_INDEX_ARG and s.flags & _abi.FBR_BODY_SUMMABLE
+    s = registry.spec("payload_map_4k")
+    assert (s.arg_bytes, s.result_bytes) == (4096, 4096) and s.result_dtype() == (np.dtype(np.uint32), (1024,))
+    fid = ctypes.c_int(-1)
+    lib = _abi.load()
+    assert lib.fbr_body_lookup(b"parzen_f64", ctypes.byref(fid)) == 0 and fid.value == registry.spec("parzen_f64").func_id
+    assert lib.fbr_body_lookup(b"no_such_body", ctypes.byref(fid)) == _abi.FBR_ENOENT
+    assert b"no_such_body" in lib.fbr_last_error()
+    with pytest.raises(KeyError):
+        registry.spec("no_such_body")
+
+
+@pytest.mark.skipif(_gpu_present(), reason="checks the no-GPU failure mode")
+def test_no_gpu_means_hard_failure_not_cpu_fallback():
+    lib = _abi.load()
+    h = ctypes.c_void_p()
+    rc = lib.fbr_pool_create(1, None, 0, 0, ctypes.byref(h))
+    assert rc == _abi.FBR_ENODEV and not h.value
+    pool = fiber_b200.Pool(2)
+    with pytest.raises(_abi.EngineError) as ei:
+        pool.map(W.f, [1, 2, 3])
+    assert ei.value.status == _abi.FBR_ENODEV
+
+
+def test_missing_library_is_a_hard_error(monkeypatch):
+    monkeypatch.setattr(_abi, "_lib", None)
+    monkeypatch.setattr(_abi, "LIB_PATH", "/nonexistent/libfiber_b200.so")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _abi.load()
+
+
+# ---- host logic: registry + encoders (what replaces pickling, fiber/pool.py:961,1181) -----------------
+def test_registry_binding_and_meta():
+    assert registry.body_name_of(W.f) == "square_i64"
+    assert W.f.__fiber_meta__ == {"gpu": 1}                      # fiber/meta.py:53-56 storage attribute
+
+    @fiber_b200.meta(cpu=4, memory=1000, gpu=1)
+    def g():
+        pass
+    assert g.__fiber_meta__ == {"cpu": 4, "mem": 1000, "gpu": 1}  # memory -> mem (fiber/meta.py:19-25)
+    with pytest.raises(AssertionError):
+        fiber_b200.meta(disk=1)
+    with pytest.raises(TypeError, match="no CPU fallback"):
+        registry.body_name_of(W.unbound)
+    with pytest.raises(TypeError):
+        registry.body_name_of(print)
+    with pytest.raises(KeyError):
+        fiber_b200.bind(lambda x: x, "not_a_body")
+    fiber_b200.bind(abs, "identity_i64")                          # builtins cannot carry attributes
+    assert registry.body_name_of(abs) == "identity_i64"
+
+
+def test_encoders_unary():
+    s = registry.spec("square_i64")
+    e = s.encode_map(range(5, 500, 7))
+    assert (e.n, e.arg_stride, e.index_start, e.index_step, e.args) == (71, 0, 5, 7, None)
+    e = s.encode_map([3, -4, 5])
+    assert e.arg_stride == 8 and e.args.dtype == np.int64 and e.args.tolist() == [3, -4, 5]
+    e = s.encode_starmap([(x,) for x in range(4)])
+    assert e.args.tolist() == [0, 1, 2, 3]
+    e = s.encode_apply((42,), {})
+    assert e.n == 1 and e.args.tolist() == [42]
+    assert s.encode_map([]).n == 0
+    with pytest.raises(OverflowError):
+        s.encode_map([2 ** 70])
+    with pytest.raises(TypeError):
+        s.encode_map([1.5])
+    with pytest.raises(TypeError):
+        s.encode_starmap([(1, 2)])
+    with pytest.raises(TypeError):
+        s.encode_apply((1,), {"y": 2})
+
+
+def test_encoders_binary_and_kwds():
+    s = registry.spec("square_scale_i64")
+    assert s.encode_apply((36,), {"y": 2}).args.tolist() == [[36, 2]]       # tests/test_pool.py:115
+    assert s.encode_apply((36,), {}).args.tolist() == [[36, 1]]             # default y=1
+    assert s.encode_starmap([(3,), (4, 5)]).args.tolist() == [[3, 1], [4, 5]]
+    m = registry.spec("mul2_i64")
+    assert m.encode_starmap([(x, x) for x in range(3)]).args.tolist() == [[0, 0], [1, 1], [2, 2]]
+    with pytest.raises(TypeError):
+        m.encode_starmap([(1,)])
+    with pytest.raises(TypeError):
+        m.encode_apply((1, 2), {"y": 3})
+
+
+def test_encoder_parzen_shared_block():
+    from oracle import bodies as B
+    xs, px, widths = B.parzen_example_inputs()
+    s = registry.spec("parzen_f32")
+    e = s.encode_starmap([(xs, px, w) for w in widths])
+    assert e.n == 102 and e.arg_stride == 8 and e.args.tolist() == [float(w) for w in widths]
+    hdr = np.frombuffer(e.shared[:80], dtype=s.HEADER)[0]
+    assert (hdr["n_samples"], hdr["dims"], hdr["power"], hdr["elem_bytes"]) == (10000, 2, 1, 4)
+    assert len(e.shared) == 80 + 10000 * 2 * 4
+    assert np.array_equal(np.frombuffer(e.shared[80:], dtype=np.float32).reshape(10000, 2), xs.astype(np.float32))
+    e64 = registry.spec("parzen_f64").encode_apply((xs, px, 0.5), {})
+    assert len(e64.shared) == 80 + 10000 * 2 * 8
+    with pytest.raises(ValueError):                   # reference: ambiguous truth value for p != 1
+        s.encode_apply((xs, np.zeros((2, 2)), 0.5), {})
+    with pytest.raises(ValueError):
+        s.encode_starmap([(xs, px, 0.1), (xs[:100], px, 0.2)])
+
+
+def test_encoder_payload():
+    from oracle import cref
+    recs = cref.payload_records(10, 4)
+    s = registry.spec("payload_map_4k")
+    e = s.encode_map(recs)
+    assert (e.n, e.arg_stride, e.task_index_base) == (4, 4096, 0) and e.args.ctypes.data == recs.ctypes.data
+    e = s.encode_starmap([(10 + i, recs[i]) for i in range(4)])
+    assert e.task_index_base == 10 and np.array_equal(e.args, recs)
+    with pytest.raises(ValueError):
+        s.encode_starmap([(0, recs[0]), (2, recs[1])])
+    with pytest.raises(TypeError):
+        s.encode_map(np.zeros((3, 100), dtype=np.uint32))
+
+
+def test_pool_argument_validation_without_device():
+    with pytest.raises(NotImplementedError):
+        fiber_b200.Pool(2, initializer=print)
+    with pytest.raises(ValueError):
+        fiber_b200.Pool(0)
+    p = fiber_b200.Pool()                                    # processes=None -> 1 (fiber/pool.py:894)
+    assert p._processes == 1
+    with pytest.raises(NotImplementedError):
+        p.map_async(W.f, [1], error_callback=print)           # fiber/pool.py:1162-1164
+    with pytest.raises(TypeError):
+        p.map(W.unbound, [1])                                 # rejected before any device work
+    p.close()
+    with pytest.raises(ValueError, match="Pool is not running"):
+        p.map(W.f, [1, 2, 3])                                 # fiber/pool.py:1166-1167
+    with pytest.raises(ValueError):
+        p.apply_async(W.f, (1,))
+    with pytest.raises(ValueError):
+        p.starmap(W.f, [(1,)])
+    p.join()
+    assert fiber_b200.active_children() == []
