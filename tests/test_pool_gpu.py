@@ -339,3 +339,54 @@ def test_multi_worker_blocks_if_available():
     assert res.sum() == count and np.array_equal(np.asarray(res).view(np.uint8), ref)
     pool.terminate()
     pool.join()
+
+
+# ---- ResilientZPool semantics (tests/test_pool.py:282-315) ---------------------------------------------
+def test_error_handling(golden):
+    pool = fiber_b200.Pool(3, error_handling=True)
+    try:
+        pool.start_workers()
+        pool.wait_until_workers_up()
+        res = pool.map(W.random_error_worker, [i for i in range(300)], chunksize=1)
+        assert res == [i for i in range(300)] == golden("pool_known_answers")["resilient_map_300_cs1"]
+        assert pool.stats()["units_redispatched"] > 0          # ~5 % of the tasks killed their worker
+    finally:
+        pool.terminate()
+        pool.join()
+
+
+def test_error_handling_unordered():
+    pool = fiber_b200.Pool(3, error_handling=True)
+    try:
+        res = list(pool.imap_unordered(W.random_error_worker, [i for i in range(300)], chunksize=1))
+        res.sort()
+        assert res == [i for i in range(300)]
+    finally:
+        pool.terminate()
+        pool.join()
+
+
+def test_error_handling_large_and_other_bodies():
+    pool = fiber_b200.Pool(1, error_handling=True, ring_bytes=1 << 20)
+    n = 1_000_003
+    res = pool.map(W.random_error_worker, range(n))              # many waves, several re-dispatch rounds
+    assert np.array_equal(np.asarray(res), np.arange(n))
+    assert res.sum() == n * (n - 1) // 2                          # lost units never double-counted
+    s = pool.stats()
+    assert s["units_redispatched"] > 0.05 * (n // 2)
+    # bodies that never fault behave exactly as in the plain pool
+    assert pool.map(W.f, range(1000)) == [i * i for i in range(1000)]
+    assert pool.starmap(W.f2, [(x, x) for x in range(100)], 10) == [x * x for x in range(100)]
+    assert pool.apply(W.fy, (36,), {"y": 2}) == 2592
+    pool.terminate()
+    pool.join()
+
+
+def test_worker_death_without_error_handling_raises():
+    """Plain ZPool: a task exception kills the worker and the map never returns
+    (fiber/pool.py:801-824).  The engine reports it instead of hanging."""
+    pool = fiber_b200.Pool(1)
+    with pytest.raises(RuntimeError, match="device error code 3"):
+        pool.map(W.random_error_worker, range(1000))
+    pool.terminate()
+    pool.join()
