@@ -286,6 +286,87 @@ def run_reference(args, dist):
     print(json.dumps(line), flush=True)
 
 
+
+def run_multi_gpu(args, dist, dev):
+    """BASELINE.json configs[3] and [4] on N GPUs (torch.distributed/NCCL is the exchange plumbing;
+    the map itself runs through the C ABI on torch-allocated device buffers):
+      * payload4k_sharded: 1e6 tasks TOTAL, contiguous block per rank (strong scaling):
+        (i) shard-resident, (ii) including NCCL scatter from rank 0 and gather to rank 0;
+      * ring_allreduce: 256 MiB fp32 all-reduce across the ring (experimental.Ring's collective)."""
+    import numpy as np
+    import torch
+    import torch.distributed as td
+    from fiber_b200 import _abi, shard
+    from fiber_b200.experimental import allreduce_bench
+    from oracle import cref
+
+    rank, world = dist.rank, dist.world
+    n_total = PAYLOAD_TASKS
+    lo, hi = shard.block_of(n_total, rank, world)
+    n_loc = hi - lo
+    width = max(b - a for a, b in shard.blocks(n_total, world))
+    cuda = torch.device("cuda", dev)
+    eng = RawEngine(dev, width * 4096 + (1 << 20))
+    inp = torch.empty(width * 1024, dtype=torch.int32, device=cuda)
+    out = torch.empty(width * 1024, dtype=torch.int32, device=cuda)
+    _abi.check(eng.lib.fbr_payload_fill_device(eng.h, 0, ctypes.c_void_p(inp.data_ptr()), lo, n_loc))
+    torch.cuda.synchronize()
+
+    def local_map():
+        seq = eng.submit("payload_map_4k", n_loc, ctypes.c_void_p(out.data_ptr()), args_dev=ctypes.c_void_p(inp.data_ptr()),
+                         arg_stride=4096, task_base=lo, want_sum=False)
+        eng.wait(seq, release=False)
+
+    for _ in range(3):
+        local_map()
+    eng.release_deferred()
+    t_res = timed_steps(dist, args.steps, 0, local_map)
+    eng.release_deferred()
+
+    # (ii) scatter from rank 0 -> map -> gather to rank 0 (root-ingress bound over NVLink)
+    full_in = full_out = None
+    if rank == 0:
+        full_in = torch.empty(world * width * 1024, dtype=torch.int32, device=cuda)
+        full_out = torch.empty(world * width * 1024, dtype=torch.int32, device=cuda)
+        for r, (a, b) in enumerate(shard.blocks(n_total, world)):
+            _abi.check(eng.lib.fbr_payload_fill_device(eng.h, 0, ctypes.c_void_p(full_in.data_ptr() + r * width * 4096), a, b - a))
+        torch.cuda.synchronize()
+
+    def scattered_map():
+        td.scatter(inp, list(full_in.chunk(world)) if rank == 0 else None, src=0)
+        torch.cuda.synchronize()
+        local_map()
+        td.gather(out, list(full_out.chunk(world)) if rank == 0 else None, dst=0)
+        torch.cuda.synchronize()
+
+    for _ in range(2):
+        scattered_map()
+    eng.release_deferred()
+    t_sc = timed_steps(dist, args.steps, 0, scattered_map)
+    eng.release_deferred()
+    ok = True
+    if rank == 0:
+        for r, (a, b) in enumerate(shard.blocks(n_total, world)):
+            got = full_out[r * width * 1024: r * width * 1024 + 8 * 1024].cpu().numpy().view(np.uint32).reshape(8, 1024)
+            ok &= bool(np.array_equal(got, cref.payload_map(a, cref.payload_records(a, 8))))
+    eng.close()
+    del inp, out, full_in, full_out
+    torch.cuda.empty_cache()
+    ar_ok, algbw, busbw, ar_ms = allreduce_bench(64 * 1024 * 1024, steps=max(5, args.steps), warmup=3, device=cuda)
+    return {
+        "payload4k_sharded": {
+            "workload": "synthetic 4 KB-payload map, %d tasks TOTAL in contiguous blocks over %d GPUs (BASELINE.json configs[3])" % (n_total, world),
+            "scaling": "strong",
+            "shard_resident": {"value": n_total * args.steps / t_res, "unit": "tasks/s", "ms_per_step": 1e3 * t_res / args.steps},
+            "scatter_map_gather_root0": {"value": n_total * args.steps / t_sc, "unit": "tasks/s", "ms_per_step": 1e3 * t_sc / args.steps,
+                                         "note": "NCCL scatter from rank 0 + map + NCCL gather to rank 0; root link-bound"},
+            "parity_spot_check": ok},
+        "ring_allreduce": {"workload": "all-reduce SUM of 64 Mi fp32 (256 MiB) per rank, %d ranks (BASELINE.json configs[4])" % world,
+                           "bit_exact": ar_ok, "algbw_GBps": algbw, "busbw_GBps": busbw, "ms": ar_ms,
+                           "nvlink_ref": "measured refs: 725 GB/s all-reduce busbw @1 GiB, 770 GB/s peer copy (B200_PROFILING.md)"},
+    }
+
+
 # ------------------------------------------------------------------------------------------------
 def run_ours(args, dist):
     import numpy as np
@@ -403,6 +484,11 @@ def run_ours(args, dist):
         eng.dfree(out2)
     eng.close()
 
+    # ---------------- N > 1: the sharded 4 KB map (config 4) and the ring all-reduce (config 5) ---------
+    multi = None
+    if world > 1 and not args.skip_payload:
+        multi = run_multi_gpu(args, dist, dev)
+
     # ---------------- e2e: the public API with host buffers ---------------------------------------------
     pool = fiber_b200.Pool(1, devices=[dev], timing=False)
     my_range = range(my_first, my_first + PI_TASKS)
@@ -457,7 +543,7 @@ def run_ours(args, dist):
             "e2e": e2e, "gpu_launches": int(launches_value + launches_e2e),
             "gpu_launches_per_step": {"value_path": launches_value / args.steps, "e2e_path": launches_e2e / args.steps},
             "roofline": roofline, "roofline_dispatch": roofline_dispatch, "payload4k": payload,
-            "cpu_baseline": cpu, "clocks": clk,
+            "multi_gpu": multi, "cpu_baseline": cpu, "clocks": clk,
             "check": {"pi_count_all_ranks": total_count, "pi_estimate": 4.0 * total_count / (world * PI_TASKS),
                       "e2e_count": e2e_counts[-1]},
             "t_list_1e6": {"tasks_per_s": 1e6 / t_list, "note": "Pool.map(...).tolist(): Python list in hand at 1e6 tasks"},
