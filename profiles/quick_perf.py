@@ -1,0 +1,42 @@
+"""Event-timed kernel times of the bench workloads (no ncu): quick A/B while tuning kernels."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from fiber_b200 import _abi  # noqa: E402
+
+PEAK = bench.load_peaks()[0]["hbm_gbs"]
+
+
+def report(tag, st):
+    d_ms = st["dispatch_ms"] / max(1, st["dispatch_launches"])
+    g_ms = st["gather_ms"] / max(1, st["gather_launches"])
+    d_b = st["dispatch_bytes"] / max(1, st["dispatch_launches"])
+    g_b = st["gather_bytes"] / max(1, st["gather_launches"])
+    print("%-10s dispatch %.4f ms (%.0f GB/s, %.1f%%)   gather %.4f ms (%.0f GB/s, %.1f%%)" % (
+        tag, d_ms, d_b / d_ms / 1e6, 100 * d_b / d_ms / 1e6 / PEAK, g_ms, g_b / g_ms / 1e6, 100 * g_b / g_ms / 1e6 / PEAK), flush=True)
+
+
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
+eng = bench.RawEngine(0, 160 << 20)
+out = eng.dalloc(bench.PI_TASKS)
+for i in range(steps + 3):
+    if i == 3:
+        eng.stats(reset=True)
+    eng.wait(eng.submit("pi_inside_det", bench.PI_TASKS, out))
+report("pi", eng.stats())
+eng.dfree(out)
+eng.close()
+n = bench.PAYLOAD_TASKS
+eng = bench.RawEngine(0, n * 4096 + (1 << 20))
+a, b = eng.dalloc(n * 4096), eng.dalloc(n * 4096)
+_abi.check(eng.lib.fbr_payload_fill_device(eng.h, 0, a, 0, n))
+for body, sumflag in (("payload_map_4k", False), ("payload_checksum_4k", True)):
+    for i in range(steps + 3):
+        if i == 3:
+            eng.stats(reset=True)
+        eng.wait(eng.submit(body, n, b, args_dev=a, arg_stride=4096, want_sum=sumflag))
+    report(body[:10], eng.stats())
+eng.close()
