@@ -15,6 +15,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "bodies.cuh"
 
@@ -113,30 +114,46 @@ __global__ void __launch_bounds__(kThreads) dispatch_thread_kernel(const WavePar
         const uint8_t* uargs = wp.args + rec.arg_off;
 
         for (uint32_t base = threadIdx.x * V; base < rec.count; base += kThreads * V) {
-            alignas(16) Res r[V];
+            // results are packed into one 16 B register vector (no local-memory staging)
+            uint32_t pk[4] = {0u, 0u, 0u, 0u};
+            // implicit range() argument: one multiply per thread, then strength-reduced adds
+            // (keeps the integer-multiply pipe for the body: Philox needs 20 IMAD.WIDE per task)
+            int64_t a_idx = 0;
+            if constexpr (B::kIndexArg) a_idx = wp.index_start + (int64_t)(rec.first + base) * wp.index_step;
+            const bool index_args = B::kIndexArg && wp.arg_stride == 0;
+            const uint64_t gidx0 = wp.index_base + rec.first + base;
 #pragma unroll
             for (int v = 0; v < V; ++v) {
                 const uint32_t i = base + v;
+                Res r = Res{};
                 if (i < rec.count) {
                     Arg a;
                     if constexpr (B::kIndexArg) {
-                        if (wp.arg_stride == 0)
-                            a = (Arg)(wp.index_start + (int64_t)(rec.first + i) * wp.index_step);
-                        else
-                            a = *reinterpret_cast<const Arg*>(uargs + (size_t)i * wp.arg_stride);
+                        if (index_args) a = (Arg)a_idx;
+                        else a = *reinterpret_cast<const Arg*>(uargs + (size_t)i * wp.arg_stride);
                     } else {
                         a = *reinterpret_cast<const Arg*>(uargs + (size_t)i * wp.arg_stride);
                     }
-                    r[v] = B::run(a, wp.index_base + rec.first + i, es, rec.attempt);
+                    r = B::run(a, gidx0 + v, es, rec.attempt);
+                }
+                if constexpr (B::kIndexArg) a_idx += wp.index_step;
+                if constexpr (sizeof(Res) == 1) {
+                    pk[v >> 2] |= (uint32_t)(uint8_t)r << ((v & 3) * 8);
+                } else if constexpr (sizeof(Res) == 8) {
+                    unsigned long long bits;
+                    memcpy(&bits, &r, 8);
+                    pk[2 * v] = (uint32_t)bits;
+                    pk[2 * v + 1] = (uint32_t)(bits >> 32);
                 } else {
-                    r[v] = Res{};
+                    static_assert(sizeof(Res) == 1 || sizeof(Res) == 8, "add a packing rule for this result size");
                 }
             }
-            Res* dst = reinterpret_cast<Res*>(slot) + base;
+            uint8_t* dst = slot + (size_t)base * sizeof(Res);
             if (base + V <= rec.count) {
-                st_vec(dst, *reinterpret_cast<const uint4*>(r));
+                st_vec(dst, make_uint4(pk[0], pk[1], pk[2], pk[3]));
             } else {
-                for (int v = 0; v < V && base + v < rec.count; ++v) dst[v] = r[v];
+                const uint32_t nb = (rec.count - base) * (uint32_t)sizeof(Res);
+                for (uint32_t b = 0; b < nb; ++b) dst[b] = (uint8_t)(pk[b >> 2] >> ((b & 3) * 8));
             }
         }
         __syncthreads();  // s_fault final

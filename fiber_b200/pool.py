@@ -68,6 +68,24 @@ class _Segment:
             eng.lib.fbr_result_release(eng.handle, self.seq)
 
 
+class _PinnedBlock:
+    """Pinned host block from the engine's segment cache (``fbr_host_alloc``): NumPy views keep it
+    alive, garbage collection returns it.  Arguments that live here are DMA'd straight to the device
+    (no staging copy) -- the host end of the pinned task ring."""
+
+    def __init__(self, engine, nbytes):
+        self.engine = engine
+        ptr = ctypes.c_void_p()
+        _abi.check(engine.lib.fbr_host_alloc(engine.handle, max(1, nbytes), ctypes.byref(ptr)))
+        self.ptr = ptr.value
+        self.__array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 3}
+
+    def __del__(self):
+        eng = getattr(self, "engine", None)
+        if eng is not None and eng.handle and getattr(self, "ptr", None):
+            eng.lib.fbr_host_free(eng.handle, ctypes.c_void_p(self.ptr))
+
+
 class ResultArray(collections.abc.Sequence):
     """Ordered results of one map, backed by the pinned result segment (no per-item Python
     objects).  Behaves like the list the reference returns: indexing, slicing, iteration, ``len``,
@@ -412,6 +430,16 @@ class Pool:
             _abi.check(self._engine.lib.fbr_pool_join(self._engine.handle))
 
     # -- extras ------------------------------------------------------------------------------------------
+    def pinned_empty(self, shape, dtype=np.uint8):
+        """NumPy array in pinned host memory owned by this pool: argument records built in it are
+        copied to the GPU by DMA without an intermediate staging copy."""
+        self.start_workers()
+        dtype = np.dtype(dtype)
+        shape = (shape,) if isinstance(shape, int) else tuple(shape)
+        nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+        block = _PinnedBlock(self._engine, nbytes)
+        return np.asarray(block).view(dtype).reshape(shape)
+
     def stats(self):
         """``fbr_pool_stats`` as a dict (extends the reference's sent_tasks/recv_tasks counters)."""
         self.start_workers()
