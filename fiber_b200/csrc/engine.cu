@@ -109,7 +109,7 @@ static const BodyEntry kBodies[F_COUNT] = {
 enum { ST_RUN = 0, ST_CLOSE = 1, ST_TERMINATE = 2 };
 constexpr int kRecWindows = 4;         // task-ring windows in flight
 constexpr uint32_t kRecCapacity = 65536;  // claim units per wave
-constexpr int kCtrlSlots = 1024;       // concurrent seqs per worker
+constexpr int kCtrlSlots = 65536;      // maps in flight (submitted, not yet released) per worker
 constexpr int kTickets = 64;
 
 struct SeqCtrl {              // per (seq, worker) control block, device + pinned mirror
@@ -139,7 +139,7 @@ struct Worker {
     uint64_t wave_no = 0;
     int occ[F_COUNT];
     int occ_gather = 1, occ_fill = 1, occ_gather_rows = 1;
-    std::vector<bool> ctrl_used;
+    std::vector<int> ctrl_free;        // free-list of control-block slots
 };
 
 struct TimedPair { cudaEvent_t a, b; };
@@ -261,7 +261,8 @@ static int worker_init(fbr_pool* p, Worker& w, int device) {
     CK(cudaMalloc((void**)&w.d_ctrl, sizeof(SeqCtrl) * kCtrlSlots));
     CK(cudaHostAlloc((void**)&w.h_ctrl, sizeof(SeqCtrl) * (kCtrlSlots + 1), cudaHostAllocPortable));
     w.h_ctrl[kCtrlSlots] = SeqCtrl{0, ~0ull, 0u, 0u};
-    w.ctrl_used.assign(kCtrlSlots, false);
+    w.ctrl_free.resize(kCtrlSlots);
+    for (int i = 0; i < kCtrlSlots; ++i) w.ctrl_free[i] = kCtrlSlots - 1 - i;
     for (int i = 0; i < kRecWindows; ++i) {
         CK(cudaEventCreateWithFlags(&w.ev_rec_h2d[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&w.ev_comp[i], cudaEventDisableTiming));
@@ -505,11 +506,9 @@ static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry
     const uint32_t unit = cx.unit, R = cx.R;
 
     // control block
-    int slot = -1;
-    for (int i = 0; i < kCtrlSlots; ++i)
-        if (!w.ctrl_used[i]) { slot = i; break; }
-    if (slot < 0) return fail(FBR_ENOMEM, "more than %d maps in flight on worker %d", kCtrlSlots, part.worker);
-    w.ctrl_used[slot] = true;
+    if (w.ctrl_free.empty()) return fail(FBR_ENOMEM, "more than %d maps in flight on worker %d", kCtrlSlots, part.worker);
+    const int slot = w.ctrl_free.back();
+    w.ctrl_free.pop_back();
     part.ctrl_slot = slot;
     CK(cudaMemcpyAsync(&w.d_ctrl[slot], &w.h_ctrl[kCtrlSlots], sizeof(SeqCtrl), cudaMemcpyHostToDevice, w.s_in));
 
@@ -676,7 +675,7 @@ static void free_seq(fbr_pool* p, SeqState& st) {
         if (part.d_args_full) cudaFree(part.d_args_full);
         if (part.d_lost) cudaFree(part.d_lost);
         if (part.h_lost) cudaFreeHost(part.h_lost);
-        if (part.ctrl_slot >= 0) w.ctrl_used[part.ctrl_slot] = false;
+        if (part.ctrl_slot >= 0) w.ctrl_free.push_back(part.ctrl_slot);
     }
     if (st.own_out && st.out) pinned_release(p, st.out);
 }

@@ -390,3 +390,12 @@ def test_worker_death_without_error_handling_raises():
         pool.map(W.random_error_worker, range(1000))
     pool.terminate()
     pool.join()
+
+
+def test_thousands_of_maps_in_flight(pool):
+    """The reference keeps any number of pending maps in its Inventory (fiber/pool.py:659-664);
+    5000 apply_async handles are submitted before the first get()."""
+    handles = [pool.apply_async(W.f, (i,)) for i in range(5000)]
+    assert [h.get() for h in handles] == [i * i for i in range(5000)]
+    maps = [pool.map_async(W.f, range(i, i + 10)) for i in range(500)]
+    assert all(m.get() == [j * j for j in range(i, i + 10)] for i, m in enumerate(maps))
