@@ -76,3 +76,29 @@ def payload_checksum(t, rec):
 
 def unbound(x):
     return x + 1
+
+
+# ---- process targets of the reference's tests/test_queue.py, bound to device process bodies ---------
+@fiber_b200.device_process("queue_worker")
+def worker(q_in, q_out, ident):            # tests/test_queue.py:44-50
+    _device_only("worker")
+
+
+@fiber_b200.device_process("put_queue")
+def put_queue(q, data):                    # tests/test_queue.py:23-33
+    _device_only("put_queue")
+
+
+@fiber_b200.device_process("get_queue")
+def get_queue(q_in, q_out, n):             # tests/test_queue.py:36-42
+    _device_only("get_queue")
+
+
+@fiber_b200.device_process("write_pipe")
+def write_pipe(pipe, msg):                 # tests/test_queue.py:19-20
+    _device_only("write_pipe")
+
+
+@fiber_b200.device_process("pipe_worker")
+def pipe_worker(conn):                     # tests/test_queue.py:53-57
+    _device_only("pipe_worker")

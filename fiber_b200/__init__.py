@@ -12,6 +12,8 @@ import multiprocessing as _mp
 
 from .meta import meta  # noqa: F401
 from .pool import ApplyResult, MapResult, Pool, ResultArray  # noqa: F401
+from .process import Process, active_children, device_process  # noqa: F401
+from .queues import Connection, Pipe, SimpleQueue  # noqa: F401
 from .registry import bind, body_names, device_body  # noqa: F401
 
 __version__ = "0.1.0"
@@ -30,8 +32,3 @@ def cpu_count():
 def current_process():
     """fiber/context.py:24: GPU workers are not OS processes, the caller is always the master."""
     return _mp.current_process()
-
-
-def active_children():
-    """fiber/context.py:25: no job-backed child processes exist on this path."""
-    return []

@@ -39,7 +39,18 @@ SYMBOLS = [
     "fbr_host_alloc", "fbr_host_free", "fbr_device_alloc", "fbr_device_free",
     "fbr_memcpy_h2d", "fbr_memcpy_d2h", "fbr_payload_fill_device",
     "fbr_pool_stats", "fbr_pool_stats_reset",
+    "fbr_queue_last_error", "fbr_queue_create", "fbr_queue_open_writer", "fbr_queue_open_reader",
+    "fbr_lane_send", "fbr_lane_recv", "fbr_lane_poll", "fbr_queue_put", "fbr_queue_get", "fbr_queue_stats",
+    "fbr_queue_destroy", "fbr_process_start", "fbr_process_poll", "fbr_process_join", "fbr_process_terminate",
+    "fbr_process_handled", "fbr_process_destroy",
 ]
+
+FBR_REC_NONE, FBR_REC_INT, FBR_REC_FLOAT, FBR_REC_BYTES, FBR_REC_STR = range(5)
+FBR_PROC_QUEUE_WORKER, FBR_PROC_PUT_QUEUE, FBR_PROC_GET_QUEUE, FBR_PROC_WRITE_PIPE, FBR_PROC_PIPE_WORKER = range(1, 6)
+
+
+class Record(ctypes.Structure):
+    _fields_ = [("tag", ctypes.c_uint32), ("len", ctypes.c_uint32), ("payload", ctypes.c_uint8 * 56)]
 
 
 class BodyInfo(ctypes.Structure):
@@ -128,6 +139,23 @@ def load():
         "fbr_payload_fill_device": (i32, [vp, i32, vp, u64, u64]),
         "fbr_pool_stats": (i32, [vp, P(Stats)]),
         "fbr_pool_stats_reset": (i32, [vp]),
+        "fbr_queue_last_error": (ctypes.c_char_p, []),
+        "fbr_queue_create": (i32, [P(vp)]),
+        "fbr_queue_open_writer": (i32, [vp, P(vp)]),
+        "fbr_queue_open_reader": (i32, [vp, P(vp)]),
+        "fbr_lane_send": (i32, [vp, P(Record), i32]),
+        "fbr_lane_recv": (i32, [vp, P(Record), i32]),
+        "fbr_lane_poll": (i32, [vp, P(i32)]),
+        "fbr_queue_put": (i32, [vp, P(Record), i32]),
+        "fbr_queue_get": (i32, [vp, P(Record), i32]),
+        "fbr_queue_stats": (i32, [vp, P(u64), P(u32), P(u32)]),
+        "fbr_queue_destroy": (i32, [vp]),
+        "fbr_process_start": (i32, [i32, i32, vp, vp, ctypes.c_int64, P(Record), P(Record), u32, i32, P(vp)]),
+        "fbr_process_poll": (i32, [vp, P(i32), P(i32)]),
+        "fbr_process_join": (i32, [vp, i32]),
+        "fbr_process_terminate": (i32, [vp]),
+        "fbr_process_handled": (i32, [vp, P(u64)]),
+        "fbr_process_destroy": (i32, [vp]),
     }
     assert sorted(sig) == sorted(SYMBOLS)
     for name, (res, args) in sig.items():
@@ -143,4 +171,11 @@ def load():
 def check(status):
     if status != FBR_OK:
         raise EngineError(status, load().fbr_last_error().decode("utf-8", "replace"))
+    return status
+
+
+def qcheck(status):
+    """Status check for the queue / process entry points (queues.cu keeps its own error string)."""
+    if status != FBR_OK:
+        raise EngineError(status, load().fbr_queue_last_error().decode("utf-8", "replace"))
     return status

@@ -521,7 +521,7 @@ static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry
         } else if (cx.args_dev) {
             cx.d_shared = (const uint8_t*)d.shared;
         } else {
-            CK(cudaMalloc(&part.d_shared_tmp, d.shared_bytes));
+            CK(cudaMallocAsync(&part.d_shared_tmp, d.shared_bytes, w.s_in));
             CK(cudaMemcpyAsync(part.d_shared_tmp, d.shared, d.shared_bytes, cudaMemcpyHostToDevice, w.s_in));
             p->stats.h2d_bytes += d.shared_bytes;
             cx.d_shared = (const uint8_t*)part.d_shared_tmp;
@@ -533,7 +533,7 @@ static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry
         cx.args_full = (const uint8_t*)d.args;
     } else if (cx.resilient && d.arg_stride) {
         // lost units may be re-dispatched at any time: keep every argument record on the device
-        CK(cudaMalloc(&part.d_args_full, std::max<uint64_t>(16, st.n_tasks * (uint64_t)d.arg_stride)));
+        CK(cudaMallocAsync(&part.d_args_full, std::max<uint64_t>(16, st.n_tasks * (uint64_t)d.arg_stride), w.s_in));
         CK(cudaMemcpyAsync((uint8_t*)part.d_args_full + part.first * (uint64_t)d.arg_stride,
                            (const uint8_t*)d.args + part.first * (uint64_t)d.arg_stride, part.count * (uint64_t)d.arg_stride,
                            cudaMemcpyHostToDevice, w.s_in));
@@ -567,13 +567,13 @@ static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry
         if (cx.out_dev) {
             cx.window_base = (uint8_t*)d.out + part.first * R;
         } else {
-            CK(cudaMalloc(&part.d_window, std::max<uint64_t>(part.count * R, 16)));
+            CK(cudaMallocAsync(&part.d_window, std::max<uint64_t>(part.count * R, 16), w.s_in));
             cx.window_base = (uint8_t*)part.d_window;
         }
     }
     if (cx.resilient) {
         part.lost_cap = (uint32_t)std::min<uint64_t>((part.count + unit - 1) / unit, 1u << 22);
-        CK(cudaMalloc((void**)&part.d_lost, sizeof(LostUnit) * std::max<uint32_t>(1, part.lost_cap)));
+        CK(cudaMallocAsync((void**)&part.d_lost, sizeof(LostUnit) * std::max<uint32_t>(1, part.lost_cap), w.s_in));
         CK(cudaHostAlloc((void**)&part.h_lost, sizeof(LostUnit) * std::max<uint32_t>(1, part.lost_cap), cudaHostAllocPortable));
     }
 
@@ -670,10 +670,12 @@ static void free_seq(fbr_pool* p, SeqState& st) {
         for (auto e : part.wave_done) cudaEventDestroy(e);
         for (auto& t : part.t_dispatch) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
         for (auto& t : part.t_gather) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
-        if (part.d_shared_tmp) cudaFree(part.d_shared_tmp);
-        if (part.d_window) cudaFree(part.d_window);
-        if (part.d_args_full) cudaFree(part.d_args_full);
-        if (part.d_lost) cudaFree(part.d_lost);
+        // stream-ordered frees: cudaFree would synchronise the whole device, i.e. wait for resident
+        // device processes (queues.cu) that may themselves be waiting for this host thread
+        if (part.d_shared_tmp) cudaFreeAsync(part.d_shared_tmp, w.s_in);
+        if (part.d_window) cudaFreeAsync(part.d_window, w.s_in);
+        if (part.d_args_full) cudaFreeAsync(part.d_args_full, w.s_in);
+        if (part.d_lost) cudaFreeAsync(part.d_lost, w.s_in);
         if (part.h_lost) cudaFreeHost(part.h_lost);
         if (part.ctrl_slot >= 0) w.ctrl_free.push_back(part.ctrl_slot);
     }

@@ -198,6 +198,52 @@ typedef struct fbr_stats {
 int fbr_pool_stats(fbr_pool_t* pool, fbr_stats_t* stats);
 int fbr_pool_stats_reset(fbr_pool_t* pool);
 
+/* ---- SimpleQueue / Pipe / device Process (fiber/queues.py:262-352, fiber/process.py:83-323) ---------
+ * Every endpoint owns one SPSC lane of 64-byte records in pinned, device-mapped memory; a queue's
+ * forwarder fair-queues its writer lanes into its reader lanes with strict round-robin (the
+ * nn_device of fiber/socket.py:297-320; tests/test_queue.py:218-250 pins 600 of 2400 messages per
+ * reader).  An endpoint is the host or a device process: a resident one-warp kernel that runs one
+ * of the reference tests' process targets against its lanes. */
+typedef struct fbr_queue fbr_queue_t;
+typedef struct fbr_lane fbr_lane_t;
+typedef struct fbr_process fbr_process_t;
+
+typedef enum fbr_record_tag { FBR_REC_NONE = 0, FBR_REC_INT = 1, FBR_REC_FLOAT = 2, FBR_REC_BYTES = 3, FBR_REC_STR = 4 } fbr_record_tag;
+typedef struct fbr_record {      /* fixed-layout message: what the reference pickles (queues.py:164-181) */
+    uint32_t tag;                /* fbr_record_tag */
+    uint32_t len;                /* payload bytes in use */
+    uint8_t payload[56];
+} fbr_record_t;
+
+typedef enum fbr_process_kind {
+    FBR_PROC_QUEUE_WORKER = 1,   /* worker(q_in, q_out, ident)      tests/test_queue.py:44-50 */
+    FBR_PROC_PUT_QUEUE = 2,      /* put_queue(q, data)              tests/test_queue.py:23-33 */
+    FBR_PROC_GET_QUEUE = 3,      /* get_queue(q_in, q_out, n)       tests/test_queue.py:36-42 */
+    FBR_PROC_WRITE_PIPE = 4,     /* write_pipe(pipe, msg)           tests/test_queue.py:19-20 */
+    FBR_PROC_PIPE_WORKER = 5     /* pipe_worker(conn)               tests/test_queue.py:53-57 */
+} fbr_process_kind;
+
+const char* fbr_queue_last_error(void);
+int fbr_queue_create(fbr_queue_t** q);                                   /* SimpleQueuePush.__init__ / Pipe */
+int fbr_queue_open_writer(fbr_queue_t* q, fbr_lane_t** lane);            /* LazyZConnection(("w", addr)) */
+int fbr_queue_open_reader(fbr_queue_t* q, fbr_lane_t** lane);            /* LazyZConnection(("r", addr)) */
+int fbr_lane_send(fbr_lane_t* lane, const fbr_record_t* rec, int timeout_ms);   /* ZConnection.send */
+int fbr_lane_recv(fbr_lane_t* lane, fbr_record_t* rec, int timeout_ms);         /* ZConnection.recv */
+int fbr_lane_poll(fbr_lane_t* lane, int* ready);                                 /* ZConnection._poll */
+int fbr_queue_put(fbr_queue_t* q, const fbr_record_t* rec, int timeout_ms);     /* SimpleQueuePush.put */
+int fbr_queue_get(fbr_queue_t* q, fbr_record_t* rec, int timeout_ms);           /* SimpleQueuePush.get */
+int fbr_queue_stats(fbr_queue_t* q, uint64_t* forwarded, uint32_t* n_writers, uint32_t* n_readers);
+int fbr_queue_destroy(fbr_queue_t* q);
+/* Process.start / is_alive+exitcode / join / terminate (fiber/process.py:187-215, 217-262). */
+int fbr_process_start(int device_id, int kind, fbr_lane_t* in, fbr_lane_t* out, int64_t ident,
+                      const fbr_record_t* msg, const fbr_record_t* list, uint32_t list_len, int idle_timeout_ms,
+                      fbr_process_t** proc);
+int fbr_process_poll(fbr_process_t* proc, int* alive, int* exitcode);
+int fbr_process_join(fbr_process_t* proc, int timeout_ms);
+int fbr_process_terminate(fbr_process_t* proc);
+int fbr_process_handled(fbr_process_t* proc, uint64_t* handled);
+int fbr_process_destroy(fbr_process_t* proc);
+
 #ifdef __cplusplus
 }
 #endif
