@@ -106,6 +106,9 @@ def load():
         raise RuntimeError(
             "fiber_b200: %s is missing -- build it with `python -m fiber_b200.build` "
             "(needs nvcc; there is no CPU fallback)" % LIB_PATH)
+    # resident device processes (queues.cu) must never meet a lazily loaded kernel: prefer eager
+    # module loading when this is the first CUDA user in the process
+    os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
     L = ctypes.CDLL(LIB_PATH)
     vp, u64, i32, u32 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32
     P = ctypes.POINTER

@@ -257,7 +257,7 @@ static int worker_init(fbr_pool* p, Worker& w, int device) {
     CK(cudaMalloc((void**)&w.d_headers, sizeof(SlotHeader) * kRecCapacity));
     CK(cudaMalloc((void**)&w.d_ring, p->ring_bytes));
     CK(cudaMalloc((void**)&w.d_tickets, sizeof(uint32_t) * kTickets * 2));
-    CK(cudaMemset(w.d_tickets, 0, sizeof(uint32_t) * kTickets * 2));
+    CK(cudaMemsetAsync(w.d_tickets, 0, sizeof(uint32_t) * kTickets * 2, w.s_comp));
     CK(cudaMalloc((void**)&w.d_ctrl, sizeof(SeqCtrl) * kCtrlSlots));
     CK(cudaHostAlloc((void**)&w.h_ctrl, sizeof(SeqCtrl) * (kCtrlSlots + 1), cudaHostAllocPortable));
     w.h_ctrl[kCtrlSlots] = SeqCtrl{0, ~0ull, 0u, 0u};
@@ -279,14 +279,17 @@ static int worker_init(fbr_pool* p, Worker& w, int device) {
     if (w.occ_gather_rows < 1) w.occ_gather_rows = 1;
     if (w.occ_gather < 1) w.occ_gather = 1;
     if (w.occ_fill < 1) w.occ_fill = 1;
-    CK(cudaDeviceSynchronize());
+    // no cudaDeviceSynchronize here: it would wait for resident device processes (queues.cu)
+    CK(cudaStreamSynchronize(w.s_comp));
     return FBR_OK;
 }
 
 static void worker_destroy(Worker& w) {
     if (w.device < 0) return;
     cudaSetDevice(w.device);
-    cudaDeviceSynchronize();
+    if (w.s_in) cudaStreamSynchronize(w.s_in);
+    if (w.s_comp) cudaStreamSynchronize(w.s_comp);
+    if (w.s_out) cudaStreamSynchronize(w.s_out);
     if (w.s_in) cudaStreamDestroy(w.s_in);
     if (w.s_comp) cudaStreamDestroy(w.s_comp);
     if (w.s_out) cudaStreamDestroy(w.s_out);
@@ -688,6 +691,23 @@ static void free_seq(fbr_pool* p, SeqState& st) {
 extern "C" {
 
 int fbr_abi_version(void) { return FBR_ABI_VERSION; }
+
+// Force-load every kernel of this library on `device`.  With CUDA's lazy module loading the first
+// launch of a kernel may synchronise the context; if a resident device process (queues.cu) is
+// spinning on a host message at that moment the two deadlock.  queues.cu calls this before it
+// starts a resident kernel.  (Internal: not part of the public header.)
+int fbr_internal_preload(int device) {
+    if (cudaSetDevice(device) != cudaSuccess) return FBR_ECUDA;
+    cudaFuncAttributes at;
+    for (int f = 0; f < F_COUNT; ++f) cudaFuncGetAttributes(&at, kBodies[f].kernel);
+    cudaFuncGetAttributes(&at, (const void*)gather_ordered_kernel<false>);
+    cudaFuncGetAttributes(&at, (const void*)gather_ordered_kernel<true>);
+    cudaFuncGetAttributes(&at, (const void*)gather_rows_kernel<false>);
+    cudaFuncGetAttributes(&at, (const void*)gather_rows_kernel<true>);
+    cudaFuncGetAttributes(&at, (const void*)payload_fill_kernel);
+    cudaGetLastError();
+    return FBR_OK;
+}
 const char* fbr_last_error(void) { return g_err.c_str(); }
 
 int fbr_device_count(int* n) {
@@ -805,7 +825,7 @@ int fbr_pool_destroy(fbr_pool_t* p) {
         for (auto& kv : p->shared)
             for (size_t i = 0; i < kv.second.d_ptr.size(); ++i) {
                 cudaSetDevice(p->workers[i].device);
-                cudaFree(kv.second.d_ptr[i]);
+                cudaFreeAsync(kv.second.d_ptr[i], p->workers[i].s_comp);
             }
         for (auto& w : p->workers) worker_destroy(w);
         for (auto& kv : p->pin_free)
@@ -824,7 +844,7 @@ int fbr_shared_put(fbr_pool_t* p, const void* host, uint64_t bytes, uint64_t* ha
     for (auto& w : p->workers) {
         CK(cudaSetDevice(w.device));
         void* dptr = nullptr;
-        CK(cudaMalloc(&dptr, bytes));
+        CK(cudaMallocAsync(&dptr, bytes, w.s_in));
         CK(cudaMemcpyAsync(dptr, host, bytes, cudaMemcpyHostToDevice, w.s_in));
         CK(cudaStreamSynchronize(w.s_in));
         sb.d_ptr.push_back(dptr);
@@ -841,9 +861,10 @@ int fbr_shared_drop(fbr_pool_t* p, uint64_t handle) {
     auto it = p->shared.find(handle);
     if (it == p->shared.end()) return fail(FBR_ENOENT, "unknown shared handle");
     for (size_t i = 0; i < it->second.d_ptr.size(); ++i) {
-        cudaSetDevice(p->workers[i].device);
-        cudaDeviceSynchronize();
-        cudaFree(it->second.d_ptr[i]);
+        Worker& w = p->workers[i];
+        cudaSetDevice(w.device);
+        cudaStreamSynchronize(w.s_comp);   // maps that read the block have been waited for by their owners
+        cudaFreeAsync(it->second.d_ptr[i], w.s_comp);
     }
     p->shared.erase(it);
     return FBR_OK;

@@ -341,6 +341,8 @@ struct fbr_process {
 // ------------------------------------------------------------------------------------------------
 // extern "C"
 // ------------------------------------------------------------------------------------------------
+extern "C" int fbr_internal_preload(int device);   // engine.cu
+
 extern "C" {
 
 int fbr_queue_create(fbr_queue_t** out) {
@@ -458,6 +460,13 @@ int fbr_process_start(int device_id, int kind, fbr_lane_t* in, fbr_lane_t* out, 
     std::unique_ptr<fbr_process> p(new fbr_process());
     p->device = device_id;
     QCK(cudaSetDevice(device_id));
+    // load every kernel of the library now: a lazy module load later would synchronise with the
+    // resident kernel started below (which may be waiting for this very host thread)
+    fbr_internal_preload(device_id);
+    {
+        cudaFuncAttributes at;
+        cudaFuncGetAttributes(&at, (const void*)device_process_kernel);
+    }
     QCK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     QCK(cudaHostAlloc((void**)&p->ctrl, sizeof(ProcCtrl), cudaHostAllocPortable | cudaHostAllocMapped));
     memset((void*)p->ctrl, 0, sizeof(ProcCtrl));
