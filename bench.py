@@ -52,6 +52,17 @@ def load_peaks():
         return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback (B200_PROFILING.md)"
 
 
+def load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
+    capture of profiles/prof_target.py (same kernels, same sizes); newest round wins."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
+    if not files:
+        return {}, None
+    with open(files[-1]) as fh:
+        return json.load(fh), os.path.relpath(files[-1], ROOT)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -385,6 +396,10 @@ def run_ours(args, dist):
 
     peaks, peak_src = load_peaks()
     hbm_peak = float(peaks["hbm_gbs"])
+    traffic, traffic_src = load_traffic()
+
+    def traffic_of(key):
+        return traffic.get(key, {}).get("dram_bytes_per_launch")
     dev = dist.local_rank
     rank, world = dist.rank, dist.world
     my_first = rank * PI_TASKS
@@ -427,7 +442,7 @@ def run_ours(args, dist):
     roofline = {"kernel": "gather_ordered_kernel<sum>", "bound": "hbm",
                 "achieved": gather_bytes / (gather_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": gather_bytes / (gather_ms * 1e-3) / 1e9 / hbm_peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic_of("gather_rows_kernel<1>@prof_pi"), "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": gather_bytes, "avg_launch_ms": gather_ms,
                 "note": "2*R*N bytes (R=1 B) per launch; the ring was just written by the dispatch kernel so part of the reads can hit L2"}
     # Philox4x32-10 + f64 compare: ~20 IMAD.WIDE-class multiplies + ~60 ALU ops per task; the bound
@@ -482,11 +497,13 @@ def run_ours(args, dist):
             "roofline_dispatch": {"kernel": "dispatch_payload_map_kernel", "bound": "hbm",
                                   "achieved": d_bytes / (d_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                   "frac": d_bytes / (d_ms * 1e-3) / 1e9 / hbm_peak, "avg_launch_ms": d_ms,
-                                  "algorithmic_bytes_per_launch": d_bytes},
+                                  "algorithmic_bytes_per_launch": d_bytes,
+                                  "traffic": traffic_of("dispatch_payload_map_kernel@prof_payload")},
             "roofline_gather": {"kernel": "gather_rows_kernel (gather_ordered fast path)", "bound": "hbm",
                                 "achieved": g_bytes / (g_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                 "frac": g_bytes / (g_ms * 1e-3) / 1e9 / hbm_peak, "avg_launch_ms": g_ms,
-                                "algorithmic_bytes_per_launch": g_bytes},
+                                "algorithmic_bytes_per_launch": g_bytes,
+                                "traffic": traffic_of("gather_rows_kernel<0>@prof_payload")},
             "parity_spot_check": ok,
         }
         eng.dfree(in_dev)

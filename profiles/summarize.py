@@ -48,6 +48,20 @@ def main():
                 w.writerow(["report"] + ["%s [%s]" % (hdr[i], units[i]) for i in idx])
             for r in rows:
                 w.writerow([rep] + [r[i] for i in idx])
+    # per-launch DRAM traffic of the hot kernels, read back by bench.py for roofline.traffic
+    import json
+    traffic = {}
+    for rep in reps:
+        hdr, units, rows = raw_rows(os.path.join(OUT, rep))
+        ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for r in rows:
+            name = r[ki].split("(")[0].replace("void ", "") + "@" + rep.replace(".ncu-rep", "")
+            tot = float(r[ri]) * scale[units[ri]] + float(r[wi]) * scale[units[wi]]
+            traffic.setdefault(name, []).append(tot)
+    with open(os.path.join(ROOT, "profiles", tag + "_traffic.json"), "w") as fh:
+        json.dump({k: {"dram_bytes_per_launch": sum(v) / len(v), "launches": len(v)} for k, v in traffic.items()}, fh, indent=1, sort_keys=True)
+        fh.write("\n")
     lp = os.path.join(OUT, "launches.csv")
     if os.path.exists(lp):
         rows = [r for r in csv.reader(open(lp)) if len(r) > 10]
