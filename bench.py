@@ -298,6 +298,55 @@ def run_reference(args, dist):
 
 
 
+
+def fused_peer_map(n_gpus, n_total, steps):
+    """Root-resident 4 KB map over an in-process pool of `n_gpus` workers: inputs and ordered outputs
+    stay on GPU 0, workers reach them through NVLink peer loads/stores inside the dispatch / gather
+    kernels (no NCCL call on the data path)."""
+    import numpy as np
+    from fiber_b200 import _abi, registry
+    from oracle import cref
+    lib = _abi.load()
+    ids = (ctypes.c_int * n_gpus)(*range(n_gpus))
+    h = ctypes.c_void_p()
+    _abi.check(lib.fbr_pool_create(n_gpus, ids, (n_total // n_gpus + 4096) * 4096, 0, ctypes.byref(h)))
+    try:
+        din, dout = ctypes.c_void_p(), ctypes.c_void_p()
+        _abi.check(lib.fbr_device_alloc(h, 0, n_total * 4096, ctypes.byref(din)))
+        _abi.check(lib.fbr_device_alloc(h, 0, n_total * 4096, ctypes.byref(dout)))
+        _abi.check(lib.fbr_payload_fill_device(h, 0, din, 0, n_total))
+        d = _abi.MapDesc()
+        d.func_id = registry.spec("payload_map_4k").func_id
+        d.flags = _abi.FBR_ARGS_DEVICE | _abi.FBR_OUT_DEVICE
+        d.n_tasks, d.arg_stride, d.args, d.out = n_total, 4096, din.value, dout.value
+        res = _abi.Result()
+
+        def step():
+            seq = ctypes.c_uint64()
+            _abi.check(lib.fbr_map_submit(h, ctypes.byref(d), ctypes.byref(seq)))
+            _abi.check(lib.fbr_result_wait(h, seq.value, -1, ctypes.byref(res)))
+            _abi.check(lib.fbr_result_release(h, seq.value))
+        for _ in range(3):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        dt = time.perf_counter() - t0
+        ok = True
+        for t in (0, n_total // 2, n_total - 8):
+            got = np.empty((8, 1024), dtype=np.uint32)
+            _abi.check(lib.fbr_memcpy_d2h(h, 0, got.ctypes.data, ctypes.c_void_p(dout.value + t * 4096), got.nbytes))
+            ok &= bool(np.array_equal(got, cref.payload_map(t, cref.payload_records(t, 8))))
+        lib.fbr_device_free(h, 0, din)
+        lib.fbr_device_free(h, 0, dout)
+        link_bytes = 2 * n_total * 4096 * (n_gpus - 1) / n_gpus      # peer loads + peer stores through GPU 0's links
+        return {"value": n_total * steps / dt, "unit": "tasks/s", "ms_per_step": 1e3 * dt / steps,
+                "root_link_GBps_each_way": link_bytes / 2 / (dt / steps) / 1e9, "parity_spot_check": ok,
+                "note": "in-process Pool(%d): args/out on GPU 0, peer loads in dispatch + peer stores in gather over NVLink" % n_gpus}
+    finally:
+        lib.fbr_pool_destroy(h)
+
+
 def run_multi_gpu(args, dist, dev):
     """BASELINE.json configs[3] and [4] on N GPUs (torch.distributed/NCCL is the exchange plumbing;
     the map itself runs through the C ABI on torch-allocated device buffers):
@@ -372,6 +421,17 @@ def run_multi_gpu(args, dist, dev):
     eng.close()
     del inp, out, full_in, full_out
     torch.cuda.empty_cache()
+
+    # (iii) the same root-resident map with scatter and gather FUSED into the kernels: one in-process
+    # pool on rank 0 drives all N GPUs; arguments and ordered output live on GPU 0, every worker's
+    # dispatch kernel loads its block and its gather kernel stores its units over NVLink peer memory.
+    fused = None
+    if rank == 0:
+        try:
+            fused = fused_peer_map(world, n_total, args.steps)
+        except Exception as e:          # e.g. the launcher restricted CUDA_VISIBLE_DEVICES per rank
+            fused = {"unavailable": "%s: %s" % (type(e).__name__, e)}
+    dist.barrier()
     ar_ok, algbw, busbw, ar_ms = allreduce_bench(64 * 1024 * 1024, steps=max(5, args.steps), warmup=3, device=cuda)
     return {
         "payload4k_sharded": {
@@ -380,6 +440,7 @@ def run_multi_gpu(args, dist, dev):
             "shard_resident": {"value": n_total * args.steps / t_res, "unit": "tasks/s", "ms_per_step": 1e3 * t_res / args.steps},
             "scatter_map_gather_root0": {"value": n_total * args.steps / t_sc, "unit": "tasks/s", "ms_per_step": 1e3 * t_sc / args.steps,
                                          "note": "NCCL scatter from rank 0 + map + NCCL gather to rank 0; root link-bound"},
+            "fused_peer_memory_root0": fused,
             "parity_spot_check": ok},
         "ring_allreduce": {"workload": "all-reduce SUM of 64 Mi fp32 (256 MiB) per rank, %d ranks (BASELINE.json configs[4])" % world,
                            "bit_exact": ar_ok, "algbw_GBps": algbw, "busbw_GBps": busbw, "ms": ar_ms,

@@ -197,6 +197,7 @@ struct fbr_pool {
     int state = ST_RUN;
     uint32_t flags = 0;
     uint64_t ring_bytes = 0;
+    bool peer_ok = false;             // every worker can load/store every other worker's memory (NVLink P2P)
     std::vector<Worker> workers;
     uint64_t next_seq = 0;
     std::unordered_map<uint64_t, std::unique_ptr<SeqState>> seqs;
@@ -773,6 +774,23 @@ int fbr_pool_create(int n_workers, const int* device_ids, uint64_t ring_bytes, u
             return rc;
         }
     }
+    // Peer access between all workers: lets one map keep its arguments / ordered output resident on
+    // worker 0 while every worker's dispatch kernel loads its block and its gather kernel stores its
+    // units straight over NVLink (scatter + gather fused into the kernels, no separate collective).
+    if (n_workers > 1) {
+        p->peer_ok = true;
+        for (int i = 0; i < n_workers && p->peer_ok; ++i)
+            for (int j = 0; j < n_workers; ++j) {
+                if (i == j) continue;
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, p->workers[i].device, p->workers[j].device);
+                if (!can) { p->peer_ok = false; break; }
+                cudaSetDevice(p->workers[i].device);
+                cudaError_t e = cudaDeviceEnablePeerAccess(p->workers[j].device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) p->peer_ok = false;
+                cudaGetLastError();
+            }
+    }
     *out = p.release();
     return FBR_OK;
 }
@@ -877,8 +895,8 @@ int fbr_map_submit(fbr_pool_t* p, const fbr_map_desc_t* d, uint64_t* seq_out) {
     if (d->func_id < 0 || d->func_id >= F_COUNT) return fail(FBR_EINVAL, "bad func_id %d", d->func_id);
     const BodyEntry& body = kBodies[d->func_id];
     const bool dev_mode = (d->flags & (FBR_ARGS_DEVICE | FBR_OUT_DEVICE)) != 0;
-    if (dev_mode && p->workers.size() != 1)
-        return fail(FBR_EINVAL, "device-resident args/out need a single-worker pool (one process per GPU)");
+    if (dev_mode && p->workers.size() != 1 && !p->peer_ok)
+        return fail(FBR_EINVAL, "device-resident args/out on a multi-worker pool need peer access between all its GPUs");
     if (d->arg_stride == 0) {
         if (!(body.flags & FBR_BODY_INDEX_ARG))
             return fail(FBR_EINVAL, "body %s needs explicit argument records (arg_stride=0)", body.name);

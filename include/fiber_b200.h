@@ -107,8 +107,10 @@ int fbr_pool_worker_device(fbr_pool_t* pool, int worker, int* device_id);
 #define FBR_STARMAP 0x1u        /* 5th field True, item = (args,)      (fiber/pool.py:1297-1301) */
 #define FBR_APPLY 0x2u          /* 5th field True, item = (args, kwds) (fiber/pool.py:1112-1113) */
 #define FBR_KIND_MASK 0x3u
-#define FBR_ARGS_DEVICE 0x10u   /* args/shared are device pointers on worker 0 (n_workers must be 1) */
-#define FBR_OUT_DEVICE 0x20u    /* out is a device pointer on worker 0 (n_workers must be 1) */
+#define FBR_ARGS_DEVICE 0x10u   /* args/shared are device pointers on worker 0; other workers of the pool read
+                                   their block through NVLink peer loads inside the dispatch kernel */
+#define FBR_OUT_DEVICE 0x20u    /* out is a device pointer on worker 0; other workers' gather kernels store
+                                   their units into it through NVLink peer stores */
 #define FBR_WANT_SUM 0x40u      /* fold sum(results) into fbr_result_t.sum (FBR_BODY_SUMMABLE) */
 #define FBR_SHUFFLE 0x80u       /* permute task records inside each wave (arrival != index order;
                                    exercises placement-by-index, fiber/pool.py:672) */

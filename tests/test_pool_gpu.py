@@ -399,3 +399,55 @@ def test_thousands_of_maps_in_flight(pool):
     assert [h.get() for h in handles] == [i * i for i in range(5000)]
     maps = [pool.map_async(W.f, range(i, i + 10)) for i in range(500)]
     assert all(m.get() == [j * j for j in range(i, i + 10)] for i, m in enumerate(maps))
+
+
+def test_multi_worker_peer_memory_gather():
+    """In-process pool over all GPUs with arguments and ordered output resident on worker 0: every
+    worker's dispatch kernel loads its block and its gather kernel stores its units over NVLink peer
+    memory (scatter and gather fused into the kernels).  Bit-exact vs the oracle."""
+    import ctypes
+    from oracle import cref
+    from fiber_b200 import registry
+    ng = fiber_b200.cpu_count()
+    if ng < 2:
+        pytest.skip("needs >= 2 GPUs")
+    pool = fiber_b200.Pool(ng)
+    pool.start_workers()
+    eng, lib = pool._engine, pool._engine.lib
+    n = 40_000
+    recs = cref.payload_records(0, n)
+    din, dout = ctypes.c_void_p(), ctypes.c_void_p()
+    _abi.check(lib.fbr_device_alloc(eng.handle, 0, recs.nbytes, ctypes.byref(din)))
+    _abi.check(lib.fbr_device_alloc(eng.handle, 0, recs.nbytes, ctypes.byref(dout)))
+    _abi.check(lib.fbr_memcpy_h2d(eng.handle, 0, din, recs.ctypes.data, recs.nbytes))
+    d = _abi.MapDesc()
+    d.func_id = registry.spec("payload_map_4k").func_id
+    d.flags = _abi.FBR_ARGS_DEVICE | _abi.FBR_OUT_DEVICE
+    d.n_tasks, d.arg_stride, d.args, d.out = n, 4096, din.value, dout.value
+    seq = ctypes.c_uint64()
+    _abi.check(lib.fbr_map_submit(eng.handle, ctypes.byref(d), ctypes.byref(seq)))
+    res = _abi.Result()
+    _abi.check(lib.fbr_result_wait(eng.handle, seq.value, -1, ctypes.byref(res)))
+    _abi.check(lib.fbr_result_release(eng.handle, seq.value))
+    got = np.empty_like(recs)
+    _abi.check(lib.fbr_memcpy_d2h(eng.handle, 0, got.ctypes.data, dout, got.nbytes))
+    assert np.array_equal(got, cref.payload_map(0, recs))
+    # pi with the ordered uint8 output + count on worker 0
+    m = 10_000_000
+    dpi = ctypes.c_void_p()
+    _abi.check(lib.fbr_device_alloc(eng.handle, 0, m, ctypes.byref(dpi)))
+    d2 = _abi.MapDesc()
+    d2.func_id = registry.spec("pi_inside_det").func_id
+    d2.flags = _abi.FBR_OUT_DEVICE | _abi.FBR_WANT_SUM
+    d2.n_tasks, d2.index_start, d2.index_step, d2.out = m, 0, 1, dpi.value
+    _abi.check(lib.fbr_map_submit(eng.handle, ctypes.byref(d2), ctypes.byref(seq)))
+    _abi.check(lib.fbr_result_wait(eng.handle, seq.value, -1, ctypes.byref(res)))
+    _abi.check(lib.fbr_result_release(eng.handle, seq.value))
+    ref, count = cref.pi_inside_range(0, m)
+    hostpi = np.empty(m, dtype=np.uint8)
+    _abi.check(lib.fbr_memcpy_d2h(eng.handle, 0, hostpi.ctypes.data, dpi, m))
+    assert res.sum == count and np.array_equal(hostpi, ref)
+    for ptr in (din, dout, dpi):
+        lib.fbr_device_free(eng.handle, 0, ptr)
+    pool.terminate()
+    pool.join()
