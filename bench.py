@@ -426,11 +426,17 @@ def run_multi_gpu(args, dist, dev):
     # pool on rank 0 drives all N GPUs; arguments and ordered output live on GPU 0, every worker's
     # dispatch kernel loads its block and its gather kernel stores its units over NVLink peer memory.
     fused = None
+    # the other ranks wait on the HOST (store key), not in an NCCL barrier: a spinning NCCL kernel on
+    # their GPUs would compete with the peer traffic being measured
+    store = td.distributed_c10d._get_default_store()
     if rank == 0:
         try:
             fused = fused_peer_map(world, n_total, args.steps)
         except Exception as e:          # e.g. the launcher restricted CUDA_VISIBLE_DEVICES per rank
             fused = {"unavailable": "%s: %s" % (type(e).__name__, e)}
+        store.set("fbr_fused_done", "1")
+    else:
+        store.wait(["fbr_fused_done"])
     dist.barrier()
     ar_ok, algbw, busbw, ar_ms = allreduce_bench(64 * 1024 * 1024, steps=max(5, args.steps), warmup=3, device=cuda)
     return {
