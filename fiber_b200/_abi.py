@@ -23,8 +23,8 @@ FBR_BODY_INDEX_ARG, FBR_BODY_NEEDS_SHARED, FBR_BODY_SUMMABLE = 0x1, 0x2, 0x4
 FBR_POOL_TIMING = 0x1
 # map flags
 FBR_MAP, FBR_STARMAP, FBR_APPLY = 0x0, 0x1, 0x2
-FBR_ARGS_DEVICE, FBR_OUT_DEVICE, FBR_WANT_SUM, FBR_SHUFFLE, FBR_FULL_WINDOW, FBR_SHARED_HANDLE, FBR_RESILIENT = \
-    0x10, 0x20, 0x40, 0x80, 0x100, 0x200, 0x400
+FBR_ARGS_DEVICE, FBR_OUT_DEVICE, FBR_WANT_SUM, FBR_SHUFFLE, FBR_FULL_WINDOW, FBR_SHARED_HANDLE, FBR_RESILIENT, \
+    FBR_RESULTS_ON_DEVICE = 0x10, 0x20, 0x40, 0x80, 0x100, 0x200, 0x400, 0x800
 # fbr_task_error
 FBR_TASK_OK, FBR_TASK_OVERFLOW, FBR_TASK_BADARG, FBR_TASK_FAULT = range(4)
 
@@ -35,7 +35,7 @@ SYMBOLS = [
     "fbr_pool_create", "fbr_pool_close", "fbr_pool_terminate", "fbr_pool_join", "fbr_pool_destroy",
     "fbr_pool_n_workers", "fbr_pool_worker_device",
     "fbr_map_submit", "fbr_shared_put", "fbr_shared_drop",
-    "fbr_result_wait", "fbr_result_poll", "fbr_result_data", "fbr_result_release",
+    "fbr_result_wait", "fbr_result_poll", "fbr_result_data", "fbr_result_fetch", "fbr_result_release",
     "fbr_host_alloc", "fbr_host_free", "fbr_device_alloc", "fbr_device_free",
     "fbr_memcpy_h2d", "fbr_memcpy_d2h", "fbr_payload_fill_device",
     "fbr_pool_stats", "fbr_pool_stats_reset",
@@ -132,6 +132,7 @@ def load():
         "fbr_result_wait": (i32, [vp, u64, i32, P(Result)]),
         "fbr_result_poll": (i32, [vp, u64, P(u64)]),
         "fbr_result_data": (i32, [vp, u64, P(vp)]),
+        "fbr_result_fetch": (i32, [vp, u64, u64, u64, vp]),
         "fbr_result_release": (i32, [vp, u64]),
         "fbr_host_alloc": (i32, [vp, u64, P(vp)]),
         "fbr_host_free": (i32, [vp, vp]),

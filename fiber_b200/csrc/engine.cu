@@ -146,7 +146,7 @@ struct TimedPair { cudaEvent_t a, b; };
 
 struct PartCtx {                          // constants of one worker's block of one map
     uint32_t unit = 0, slot_stride = 0, R = 0, sum_kind = 0;
-    bool args_dev = false, out_dev = false, full_window = false, host_args = false, resilient = false;
+    bool args_dev = false, out_dev = false, full_window = false, host_args = false, resilient = false, keep_on_device = false;
     const uint8_t* d_shared = nullptr;
     uint8_t* window_base = nullptr;       // device output of a FULL_WINDOW part
     const uint8_t* args_full = nullptr;   // device-resident arguments of the whole map (args_dev / resilient)
@@ -480,7 +480,7 @@ static int finish_round(fbr_pool* p, SeqState& st, SeqPart& part, bool copy_wind
     const int slot = part.ctrl_slot;
     const int last_rw = (int)((w.wave_no - 1) % kRecWindows);
     CK(cudaStreamWaitEvent(w.s_out, w.ev_comp[last_rw], 0));
-    if (copy_window && cx.full_window && !cx.out_dev && part.count) {
+    if (copy_window && cx.full_window && !cx.out_dev && !cx.keep_on_device && part.count) {
         CK(cudaMemcpyAsync((uint8_t*)st.out + part.first * cx.R, cx.window_base, part.count * cx.R, cudaMemcpyDeviceToHost, w.s_out));
         p->stats.d2h_bytes += part.count * cx.R;
     }
@@ -502,7 +502,8 @@ static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry
     cx.resilient = (d.flags & FBR_RESILIENT) != 0;
     cx.args_dev = (d.flags & FBR_ARGS_DEVICE) != 0;
     cx.out_dev = (d.flags & FBR_OUT_DEVICE) != 0;
-    cx.full_window = cx.out_dev || cx.resilient || (d.flags & FBR_FULL_WINDOW);
+    cx.keep_on_device = (d.flags & FBR_RESULTS_ON_DEVICE) != 0;
+    cx.full_window = cx.out_dev || cx.resilient || cx.keep_on_device || (d.flags & FBR_FULL_WINDOW);
     cx.host_args = d.arg_stride != 0 && !cx.args_dev && !cx.resilient;
     const uint32_t cs = d.chunksize ? d.chunksize : 32u;
     cx.unit = pick_unit(body, cs, part.count, w.sm_count);
@@ -910,6 +911,8 @@ int fbr_map_submit(fbr_pool_t* p, const fbr_map_desc_t* d, uint64_t* seq_out) {
     if ((body.flags & FBR_BODY_NEEDS_SHARED) && (!d->shared || d->shared_bytes < sizeof(ParzenShared)))
         return fail(FBR_EINVAL, "body %s needs a shared argument block", body.name);
     if ((d->flags & FBR_OUT_DEVICE) && !d->out) return fail(FBR_EINVAL, "FBR_OUT_DEVICE without out");
+    if ((d->flags & FBR_RESULTS_ON_DEVICE) && ((d->flags & FBR_OUT_DEVICE) || d->out))
+        return fail(FBR_EINVAL, "FBR_RESULTS_ON_DEVICE owns its output buffer: do not pass out / FBR_OUT_DEVICE");
     if ((d->flags & FBR_RESILIENT) && (d->flags & FBR_SHUFFLE)) return fail(FBR_EINVAL, "FBR_RESILIENT cannot be combined with FBR_SHUFFLE");
     if ((d->flags & FBR_WANT_SUM) && !(body.flags & FBR_BODY_SUMMABLE))
         return fail(FBR_EINVAL, "body %s results cannot be summed", body.name);
@@ -923,7 +926,7 @@ int fbr_map_submit(fbr_pool_t* p, const fbr_map_desc_t* d, uint64_t* seq_out) {
     st->result_kind = body.result_kind;
     st->out = d->out;
     st->desc = *d;
-    if (!st->out && d->n_tasks) {
+    if (!st->out && d->n_tasks && !(d->flags & FBR_RESULTS_ON_DEVICE)) {
         int rc = pinned_acquire(p, d->n_tasks * body.result_bytes, &st->out);
         if (rc != FBR_OK) return rc;
         st->own_out = true;
@@ -1080,6 +1083,32 @@ int fbr_result_data(fbr_pool_t* p, uint64_t seq, void** data) {
     auto it = p->seqs.find(seq);
     if (it == p->seqs.end()) return fail(FBR_ENOENT, "unknown seq %llu", (unsigned long long)seq);
     *data = it->second->out;
+    return FBR_OK;
+}
+
+int fbr_result_fetch(fbr_pool_t* p, uint64_t seq, uint64_t first, uint64_t count, void* host_dst) {
+    if (!p || (!host_dst && count)) return fail(FBR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> g(p->mu);
+    auto it = p->seqs.find(seq);
+    if (it == p->seqs.end()) return fail(FBR_ENOENT, "unknown seq %llu", (unsigned long long)seq);
+    SeqState& st = *it->second;
+    if (!(st.flags & FBR_RESULTS_ON_DEVICE)) return fail(FBR_EINVAL, "seq %llu does not keep its results on the device", (unsigned long long)seq);
+    if (first + count > st.n_tasks) return fail(FBR_EINVAL, "range out of bounds");
+    const uint64_t R = st.result_bytes;
+    for (auto& part : st.parts) {
+        const uint64_t lo = std::max(first, part.first), hi = std::min(first + count, part.first + part.count);
+        if (lo >= hi) continue;
+        Worker& w = p->workers[part.worker];
+        CK(cudaSetDevice(w.device));
+        CK(cudaEventSynchronize(part.done));
+        CK(cudaMemcpyAsync((uint8_t*)host_dst + (lo - first) * R, part.cx.window_base + (lo - part.first) * R, (hi - lo) * R,
+                           cudaMemcpyDeviceToHost, w.s_out));
+        p->stats.d2h_bytes += (hi - lo) * R;
+    }
+    for (auto& part : st.parts) {
+        CK(cudaSetDevice(p->workers[part.worker].device));
+        CK(cudaStreamSynchronize(p->workers[part.worker].s_out));
+    }
     return FBR_OK;
 }
 

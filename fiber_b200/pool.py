@@ -90,24 +90,50 @@ class ResultArray(collections.abc.Sequence):
     """Ordered results of one map, backed by the pinned result segment (no per-item Python
     objects).  Behaves like the list the reference returns: indexing, slicing, iteration, ``len``,
     ``==`` against lists; ``tolist()`` materialises it; ``sum()`` returns the device-side sum folded
-    by ``gather_ordered`` when available."""
+    by ``gather_ordered`` when available.
 
-    def __init__(self, spec, array, device_sum=None):
+    With ``Pool(results="device")`` the ordered results stay in HBM: ``sum()`` and ``len()`` cost
+    nothing, indexing fetches just the requested range, and the full array crosses PCIe only when
+    something needs all of it (``array``, ``tolist()``, iteration, ``==``)."""
+
+    def __init__(self, spec, array, device_sum=None, n=None, fetch=None):
         self._spec = spec
-        self._a = array
+        self._arr = array
         self._sum = device_sum
+        self._n = len(array) if array is not None else n
+        self._fetch = fetch            # (lo, hi) -> ndarray, for device-resident results
+
+    @property
+    def _a(self):
+        if self._arr is None:
+            self._arr = self._fetch(0, self._n)
+        return self._arr
+
+    @property
+    def on_device(self):
+        return self._arr is None
 
     def __len__(self):
-        return len(self._a)
+        return self._n
 
     def __getitem__(self, i):
+        if self._arr is None:
+            if isinstance(i, slice):
+                lo, hi, step = i.indices(self._n)
+                if step == 1:
+                    return self._spec.rows_to_list(self._fetch(lo, max(lo, hi)))
+            else:
+                j = i + self._n if i < 0 else i
+                if not 0 <= j < self._n:
+                    raise IndexError("ResultArray index out of range")
+                return self._spec.to_python(self._fetch(j, j + 1)[0])
         if isinstance(i, slice):
             return self._spec.rows_to_list(self._a[i])
         return self._spec.to_python(self._a[i])
 
     def __iter__(self):
         step = 1 << 16
-        for s in range(0, len(self._a), step):
+        for s in range(0, self._n, step):
             yield from self._spec.rows_to_list(self._a[s:s + step])
 
     def __eq__(self, other):
@@ -120,7 +146,8 @@ class ResultArray(collections.abc.Sequence):
     def __repr__(self):
         n = len(self)
         head = self[:6]
-        return "ResultArray(%s%s, len=%d, body=%s)" % (head, "..." if n > 6 else "", n, self._spec.name)
+        return "ResultArray(%s%s, len=%d, body=%s%s)" % (head, "..." if n > 6 else "", n, self._spec.name,
+                                                         ", on device" if self._arr is None else "")
 
     def __array__(self, dtype=None, copy=None):
         a = self._a
@@ -128,7 +155,7 @@ class ResultArray(collections.abc.Sequence):
 
     @property
     def array(self):
-        """Zero-copy NumPy view of the pinned result segment."""
+        """Zero-copy NumPy view of the pinned result segment (fetches device-resident results)."""
         return self._a
 
     def tolist(self):
@@ -173,12 +200,24 @@ class MapResult:
         self._keepalive = None
         self._pool.recv_tasks += self._n
         dtype, sub = self._spec.result_dtype()
+        dsum = int(res.sum) if (self._flags & _abi.FBR_WANT_SUM) else None
+        self.n_waves = res.n_waves
+        if self._flags & _abi.FBR_RESULTS_ON_DEVICE:
+            seg = _Segment(eng, self._seq, None, 0)          # owns the seq (device buffer) until GC
+            rb, seq = res.result_bytes, self._seq
+
+            def fetch(lo, hi, seg=seg):
+                block = _PinnedBlock(eng, max(1, (hi - lo) * rb))
+                if hi > lo:
+                    _abi.check(eng.lib.fbr_result_fetch(eng.handle, seq, lo, hi - lo, ctypes.c_void_p(block.ptr)))
+                return np.asarray(block)[: (hi - lo) * rb].view(dtype).reshape((hi - lo,) + sub)
+            self._segment = seg
+            self._result = ResultArray(self._spec, None, dsum, n=int(res.n_tasks), fetch=fetch)
+            return self._result
         seg = _Segment(eng, self._seq, res.data, res.n_tasks * res.result_bytes)
         arr = np.asarray(seg).view(dtype).reshape((res.n_tasks,) + sub)
         self._segment = seg
-        dsum = int(res.sum) if (self._flags & _abi.FBR_WANT_SUM) else None
         self._result = ResultArray(self._spec, arr, dsum)
-        self.n_waves = res.n_waves
         return self._result
 
     def _raise_task_error(self, res):
@@ -198,6 +237,9 @@ class MapResult:
     def _iter_ready(self):
         """Yield results as ordered prefixes become final (per-wave completion events)."""
         if self._n == 0:
+            return
+        if self._flags & _abi.FBR_RESULTS_ON_DEVICE:
+            yield from self._wait()
             return
         eng = self._engine
         done = ctypes.c_uint64(0)
@@ -244,7 +286,7 @@ class Pool:
     """B200-native drop-in for ``fiber.Pool`` on the map/starmap/apply path."""
 
     def __init__(self, processes=None, initializer=None, initargs=(), maxtasksperchild=None,
-                 error_handling=False, *, devices=None, ring_bytes=0, timing=False):
+                 error_handling=False, *, devices=None, ring_bytes=0, timing=False, results="host"):
         self._processes = processes if processes is not None else 1   # fiber/pool.py:894
         if self._processes < 1:
             raise ValueError("Number of processes must be at least 1")
@@ -258,6 +300,9 @@ class Pool:
         self._devices = list(devices) if devices is not None else None
         self._ring_bytes = int(ring_bytes)
         self._timing = bool(timing)
+        if results not in ("host", "device"):
+            raise ValueError("results must be 'host' (pinned result segment) or 'device' (stay in HBM, fetched lazily)")
+        self._results_on_device = results == "device"
         self._state = RUN
         self._engine = None
         self._worker_handler_started = False
@@ -332,6 +377,8 @@ class Pool:
         d = _abi.MapDesc()
         d.func_id = spec.func_id
         flags = kind | extra_flags
+        if self._results_on_device:
+            flags |= _abi.FBR_RESULTS_ON_DEVICE
         if self._error_handling:
             # ResilientZPool (fiber/context.py:42-43): units whose worker dies are re-dispatched
             flags |= _abi.FBR_RESILIENT

@@ -117,6 +117,9 @@ int fbr_pool_worker_device(fbr_pool_t* pool, int worker, int* device_id);
 #define FBR_FULL_WINDOW 0x100u  /* keep the whole ordered output resident on the device until the
                                    map completes (needed when units may be re-dispatched) */
 #define FBR_SHARED_HANDLE 0x200u /* `shared` is a handle from fbr_shared_put, not a pointer */
+#define FBR_RESULTS_ON_DEVICE 0x800u /* keep the ordered results in an engine-owned device buffer (per
+                                   worker block); nothing but the 24-byte control block crosses PCIe
+                                   until fbr_result_fetch asks for a range */
 #define FBR_RESILIENT 0x400u    /* ResilientZPool semantics (fiber/pool.py:1425-1688): a claim unit whose
                                    worker dies (FBR_TASK_FAULT) is re-dispatched until it completes */
 
@@ -171,6 +174,8 @@ int fbr_result_wait(fbr_pool_t* pool, uint64_t seq, int timeout_ms, fbr_result_t
 int fbr_result_poll(fbr_pool_t* pool, uint64_t seq, uint64_t* n_done);
 /* Address of the map's ordered-result buffer without waiting: tasks [0, n_done) of it are final. */
 int fbr_result_data(fbr_pool_t* pool, uint64_t seq, void** data);
+/* Copy results [first, first+count) of a FBR_RESULTS_ON_DEVICE map to host memory (blocking). */
+int fbr_result_fetch(fbr_pool_t* pool, uint64_t seq, uint64_t first, uint64_t count, void* host_dst);
 int fbr_result_release(fbr_pool_t* pool, uint64_t seq);
 
 /* ---- memory helpers ------------------------------------------------------------------------

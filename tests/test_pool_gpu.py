@@ -451,3 +451,34 @@ def test_multi_worker_peer_memory_gather():
         lib.fbr_device_free(eng.handle, 0, ptr)
     pool.terminate()
     pool.join()
+
+
+def test_results_on_device_are_fetched_lazily(golden):
+    """Pool(results="device"): the ordered results stay in HBM; sum()/len() cross no result bytes,
+    indexing fetches ranges, full materialisation matches the host-result pool bit for bit."""
+    from oracle import cref
+    g = golden("pi_inside_det")
+    pool = fiber_b200.Pool(1, results="device")
+    n = g["n"]
+    res = pool.map(W.is_inside, range(n))
+    d2h_before = pool.stats()["d2h_bytes"]
+    assert res.on_device and len(res) == n and res.sum() == g["count"]
+    assert pool.stats()["d2h_bytes"] == d2h_before                     # nothing fetched yet
+    assert res[0] == bool(g["head_256"][0]) and res[-1] in (True, False)
+    assert res[:256] == [bool(v) for v in g["head_256"]] and res.on_device
+    assert pool.stats()["d2h_bytes"] - d2h_before < 4096
+    arr = np.asarray(res).view(np.uint8)                                # full fetch
+    assert not res.on_device and hashlib.sha256(arr.tobytes()).hexdigest() == g["sha256_uint8"]
+    assert pool.map(W.f, range(1000)) == [i * i for i in range(1000)]
+    assert list(pool.imap(W.f, range(100))) == [i * i for i in range(100)]
+    assert pool.apply(W.fy, (36,), {"y": 2}) == 2592
+    rp = fiber_b200.Pool(1, results="device", error_handling=True)
+    r = rp.map(W.random_error_worker, range(100000))
+    assert r.sum() == 100000 * 99999 // 2 and np.array_equal(np.asarray(r), np.arange(100000))
+    if fiber_b200.cpu_count() >= 2:
+        mp = fiber_b200.Pool(fiber_b200.cpu_count(), results="device")
+        r = mp.map(W.is_inside, range(5_000_000))
+        ref, count = cref.pi_inside_range(0, 5_000_000)
+        assert r.sum() == count and np.array_equal(np.asarray(r).view(np.uint8), ref)
+    with pytest.raises(ValueError):
+        fiber_b200.Pool(1, results="disk")
