@@ -169,13 +169,13 @@ class Dist:
 # raw C-ABI steps with device-resident buffers (the `value` measurement)
 # ------------------------------------------------------------------------------------------------
 class RawEngine:
-    def __init__(self, device, ring_bytes):
+    def __init__(self, device, ring_bytes, flags=0):
         from fiber_b200 import _abi, registry
         self.abi, self.registry = _abi, registry
         self.lib = _abi.load()
         ids = (ctypes.c_int * 1)(device)
         self.h = ctypes.c_void_p()
-        _abi.check(self.lib.fbr_pool_create(1, ids, ring_bytes, _abi.FBR_POOL_TIMING, ctypes.byref(self.h)))
+        _abi.check(self.lib.fbr_pool_create(1, ids, ring_bytes, _abi.FBR_POOL_TIMING | flags, ctypes.byref(self.h)))
         self.deferred = []
 
     def dalloc(self, nbytes):

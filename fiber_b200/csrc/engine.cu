@@ -77,30 +77,31 @@ struct BodyEntry {
     launch_fn launch;
     const void* kernel;
     int max_ctas_per_sm;   // 0 = as many as fit; streaming read+write bodies run best with few, fat streams
+    bool overlap_gather;   // ALU-bound body: run gather(w) concurrently with dispatch(w+1) (second stream)
 };
 
 static const BodyEntry kBodies[F_COUNT] = {
     {"square_i64", 8, 8, FBR_RES_I64, FBR_BODY_INDEX_ARG | FBR_BODY_SUMMABLE, 4096, launch_thread<SquareI64>,
-     (const void*)dispatch_thread_kernel<SquareI64>, 0},
+     (const void*)dispatch_thread_kernel<SquareI64>, 0, false},
     {"mul2_i64", 16, 8, FBR_RES_I64, FBR_BODY_SUMMABLE, 4096, launch_thread<Mul2I64>,
-     (const void*)dispatch_thread_kernel<Mul2I64>, 0},
+     (const void*)dispatch_thread_kernel<Mul2I64>, 0, false},
     {"square_scale_i64", 16, 8, FBR_RES_I64, FBR_BODY_SUMMABLE, 4096, launch_thread<SquareScaleI64>,
-     (const void*)dispatch_thread_kernel<SquareScaleI64>, 0},
+     (const void*)dispatch_thread_kernel<SquareScaleI64>, 0, false},
     {"identity_i64", 8, 8, FBR_RES_I64, FBR_BODY_INDEX_ARG | FBR_BODY_SUMMABLE, 4096, launch_thread<IdentityI64>,
-     (const void*)dispatch_thread_kernel<IdentityI64>, 0},
+     (const void*)dispatch_thread_kernel<IdentityI64>, 0, false},
     {"pi_inside_det", 8, 1, FBR_RES_BOOL, FBR_BODY_INDEX_ARG | FBR_BODY_SUMMABLE, 4096, launch_thread<PiInsideDet>,
-     (const void*)dispatch_thread_kernel<PiInsideDet>, 0},
+     (const void*)dispatch_thread_kernel<PiInsideDet>, 0, true},
     {"parzen_f32", 8, 16, FBR_RES_F64X2, FBR_BODY_NEEDS_SHARED, 1, launch_parzen<float>,
-     (const void*)dispatch_parzen_kernel<float>, 0},
+     (const void*)dispatch_parzen_kernel<float>, 0, false},
     {"parzen_f64", 8, 16, FBR_RES_F64X2, FBR_BODY_NEEDS_SHARED, 1, launch_parzen<double>,
-     (const void*)dispatch_parzen_kernel<double>, 0},
+     (const void*)dispatch_parzen_kernel<double>, 0, false},
     {"payload_map_4k", 4096, 4096, FBR_RES_BYTES, 0, 32, launch_payload_map, (const void*)dispatch_payload_map_kernel,
-     3 /* measured: 3 CTAs/SM = 6641 GB/s, 8 CTAs/SM = 6296 GB/s on the 8.2 GB wave */},
+     3 /* measured: 3 CTAs/SM = 6641 GB/s, 8 CTAs/SM = 6296 GB/s on the 8.2 GB wave */, false},
     {"payload_checksum_4k", 4096, 4, FBR_RES_U32, FBR_BODY_SUMMABLE, 256, launch_payload_checksum,
-     (const void*)dispatch_payload_checksum_kernel, 0},
-    {"sleep_f64", 8, 1, FBR_RES_NONE, 0, 1, launch_thread<SleepF64>, (const void*)dispatch_thread_kernel<SleepF64>, 0},
+     (const void*)dispatch_payload_checksum_kernel, 0, false},
+    {"sleep_f64", 8, 1, FBR_RES_NONE, 0, 1, launch_thread<SleepF64>, (const void*)dispatch_thread_kernel<SleepF64>, 0, false},
     {"fault_identity_i64", 8, 8, FBR_RES_I64, FBR_BODY_INDEX_ARG | FBR_BODY_SUMMABLE, 2, launch_thread<FaultIdentityI64>,
-     (const void*)dispatch_thread_kernel<FaultIdentityI64>, 0},
+     (const void*)dispatch_thread_kernel<FaultIdentityI64>, 0, false},
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -124,6 +125,8 @@ struct Worker {
     int device = -1;
     int sm_count = 0;
     cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
+    cudaStream_t s_gath = nullptr;         // higher-priority stream for gathers that overlap the next dispatch
+    bool prev_wave_overlap = false;        // the previous wave used only its half of the ring
     TaskRecord* h_records = nullptr;   // pinned task ring: kRecWindows x kRecCapacity
     TaskRecord* d_records = nullptr;   // device mirror
     SlotHeader* d_headers = nullptr;   // kRecCapacity
@@ -135,6 +138,7 @@ struct Worker {
     SeqCtrl* h_ctrl = nullptr;         // pinned: [0,kCtrlSlots) results, [kCtrlSlots] init pattern
     cudaEvent_t ev_rec_h2d[kRecWindows];   // window's H2D finished (host may rewrite the pinned window)
     cudaEvent_t ev_comp[kRecWindows];      // wave's kernels finished (device window / arg half reusable)
+    cudaEvent_t ev_disp[kRecWindows];      // wave's dispatch kernel finished (its gather may start)
     cudaEvent_t ev_out[2];                 // out half's D2H finished
     uint64_t wave_no = 0;
     int occ[F_COUNT];
@@ -147,6 +151,7 @@ struct TimedPair { cudaEvent_t a, b; };
 struct PartCtx {                          // constants of one worker's block of one map
     uint32_t unit = 0, slot_stride = 0, R = 0, sum_kind = 0;
     bool args_dev = false, out_dev = false, full_window = false, host_args = false, resilient = false, keep_on_device = false;
+    bool overlap = false;                 // gather(w) on s_gath concurrently with dispatch(w+1); ring used in halves
     const uint8_t* d_shared = nullptr;
     uint8_t* window_base = nullptr;       // device output of a FULL_WINDOW part
     const uint8_t* args_full = nullptr;   // device-resident arguments of the whole map (args_dev / resilient)
@@ -253,9 +258,14 @@ static int worker_init(fbr_pool* p, Worker& w, int device) {
     CK(cudaStreamCreateWithFlags(&w.s_in, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&w.s_comp, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&w.s_out, cudaStreamNonBlocking));
+    {
+        int lo_prio = 0, hi_prio = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+        CK(cudaStreamCreateWithPriority(&w.s_gath, cudaStreamNonBlocking, hi_prio));
+    }
     CK(cudaHostAlloc((void**)&w.h_records, sizeof(TaskRecord) * kRecCapacity * kRecWindows, cudaHostAllocPortable));
     CK(cudaMalloc((void**)&w.d_records, sizeof(TaskRecord) * kRecCapacity * kRecWindows));
-    CK(cudaMalloc((void**)&w.d_headers, sizeof(SlotHeader) * kRecCapacity));
+    CK(cudaMalloc((void**)&w.d_headers, sizeof(SlotHeader) * kRecCapacity * 2));   // two halves (overlapped waves)
     CK(cudaMalloc((void**)&w.d_ring, p->ring_bytes));
     CK(cudaMalloc((void**)&w.d_tickets, sizeof(uint32_t) * kTickets * 2));
     CK(cudaMemsetAsync(w.d_tickets, 0, sizeof(uint32_t) * kTickets * 2, w.s_comp));
@@ -267,6 +277,7 @@ static int worker_init(fbr_pool* p, Worker& w, int device) {
     for (int i = 0; i < kRecWindows; ++i) {
         CK(cudaEventCreateWithFlags(&w.ev_rec_h2d[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&w.ev_comp[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&w.ev_disp[i], cudaEventDisableTiming));
     }
     for (int i = 0; i < 2; ++i) CK(cudaEventCreateWithFlags(&w.ev_out[i], cudaEventDisableTiming));
     for (int f = 0; f < F_COUNT; ++f) {
@@ -291,6 +302,7 @@ static void worker_destroy(Worker& w) {
     if (w.s_in) cudaStreamSynchronize(w.s_in);
     if (w.s_comp) cudaStreamSynchronize(w.s_comp);
     if (w.s_out) cudaStreamSynchronize(w.s_out);
+    if (w.s_gath) { cudaStreamSynchronize(w.s_gath); cudaStreamDestroy(w.s_gath); }
     if (w.s_in) cudaStreamDestroy(w.s_in);
     if (w.s_comp) cudaStreamDestroy(w.s_comp);
     if (w.s_out) cudaStreamDestroy(w.s_out);
@@ -308,6 +320,7 @@ static void worker_destroy(Worker& w) {
     for (int i = 0; i < kRecWindows; ++i) {
         cudaEventDestroy(w.ev_rec_h2d[i]);
         cudaEventDestroy(w.ev_comp[i]);
+        cudaEventDestroy(w.ev_disp[i]);
     }
     for (int i = 0; i < 2; ++i) cudaEventDestroy(w.ev_out[i]);
     w.device = -1;
@@ -373,13 +386,23 @@ static int run_wave(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry& b
     }
     CK(cudaEventRecord(w.ev_rec_h2d[rw], w.s_in));
 
-    // compute stream: dispatch + gather
+    // compute streams: dispatch on s_comp; gather on s_comp too, or -- overlapped waves -- on the
+    // higher-priority s_gath so that it runs while the next wave's dispatch kernel computes.
+    // Overlapped waves use alternating halves of the ring / header array.
+    const bool ov = cx.overlap;
+    cudaStream_t s_g = ov ? w.s_gath : w.s_comp;
+    uint8_t* ring_base = ov ? w.d_ring + (size_t)half * (p->ring_bytes / 2) : w.d_ring;
+    SlotHeader* hdr_base = ov ? w.d_headers + (size_t)half * kRecCapacity : w.d_headers;
     CK(cudaStreamWaitEvent(w.s_comp, w.ev_rec_h2d[rw], 0));
+    // the ring region this dispatch writes must have been drained by the gather that last read it
+    if (wno >= 1 && !(ov && w.prev_wave_overlap)) CK(cudaStreamWaitEvent(w.s_comp, w.ev_comp[(wno - 1) % kRecWindows], 0));
+    if (wno >= 2) CK(cudaStreamWaitEvent(w.s_comp, w.ev_comp[(wno - 2) % kRecWindows], 0));
+    w.prev_wave_overlap = ov;
     if (!cx.full_window) CK(cudaStreamWaitEvent(w.s_comp, w.ev_out[half], 0));  // out half drained
     WaveParams wp;
     wp.records = drec;
-    wp.headers = w.d_headers;
-    wp.ring = w.d_ring;
+    wp.headers = hdr_base;
+    wp.ring = ring_base;
     wp.ticket = w.d_tickets + (wno % kTickets);
     wp.n_units = n_units;
     wp.slot_stride = cx.slot_stride;
@@ -394,6 +417,7 @@ static int run_wave(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry& b
     wp.resilient = cx.resilient ? 1u : 0u;
     int occ_d = w.occ[st.func_id];
     if (body.max_ctas_per_sm) occ_d = std::min(occ_d, body.max_ctas_per_sm);
+    if (ov && occ_d > 1) occ_d -= 1;     // leave SM slots for the concurrently running gather CTAs
     if (const char* e = getenv("FBR_DISPATCH_OCC")) occ_d = std::max(1, std::min(occ_d, atoi(e)));
     const int grid_d = (int)std::min<uint64_t>(n_units, (uint64_t)w.sm_count * occ_d);
     TimedPair td{nullptr, nullptr}, tg{nullptr, nullptr};
@@ -404,11 +428,16 @@ static int run_wave(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry& b
     }
     body.launch(wp, grid_d, w.s_comp);
     CK(cudaGetLastError());
-    if (timing) { CK(cudaEventRecord(td.b, w.s_comp)); CK(cudaEventRecord(tg.a, w.s_comp)); }
+    if (timing) CK(cudaEventRecord(td.b, w.s_comp));
+    if (ov) {
+        CK(cudaEventRecord(w.ev_disp[rw], w.s_comp));
+        CK(cudaStreamWaitEvent(s_g, w.ev_disp[rw], 0));
+    }
+    if (timing) CK(cudaEventRecord(tg.a, s_g));
 
     GatherParams gp;
-    gp.headers = w.d_headers;
-    gp.ring = w.d_ring;
+    gp.headers = hdr_base;
+    gp.ring = ring_base;
     gp.n_units = n_units;
     gp.slot_stride = cx.slot_stride;
     gp.result_bytes = cx.R;
@@ -436,18 +465,18 @@ static int run_wave(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry& b
         const uint32_t group_slots = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((128u << 10) / cx.slot_stride, n_units / (4 * max_ctas)));
         const uint32_t n_groups = (n_units + group_slots - 1) / group_slots;
         const int grid_r = (int)std::min<uint64_t>(n_groups, max_ctas);
-        if (cx.sum_kind) gather_rows_kernel<true><<<grid_r, kThreads, 0, w.s_comp>>>(gp, gticket, group_slots);
-        else gather_rows_kernel<false><<<grid_r, kThreads, 0, w.s_comp>>>(gp, gticket, group_slots);
-        CK(cudaMemsetAsync(gticket, 0, sizeof(uint32_t), w.s_comp));
-    } else if (cx.sum_kind) gather_ordered_kernel<true><<<grid_g, kThreads, 0, w.s_comp>>>(gp);
-    else gather_ordered_kernel<false><<<grid_g, kThreads, 0, w.s_comp>>>(gp);
+        if (cx.sum_kind) gather_rows_kernel<true><<<grid_r, kThreads, 0, s_g>>>(gp, gticket, group_slots);
+        else gather_rows_kernel<false><<<grid_r, kThreads, 0, s_g>>>(gp, gticket, group_slots);
+        CK(cudaMemsetAsync(gticket, 0, sizeof(uint32_t), s_g));
+    } else if (cx.sum_kind) gather_ordered_kernel<true><<<grid_g, kThreads, 0, s_g>>>(gp);
+    else gather_ordered_kernel<false><<<grid_g, kThreads, 0, s_g>>>(gp);
     CK(cudaGetLastError());
     if (timing) {
-        CK(cudaEventRecord(tg.b, w.s_comp));
+        CK(cudaEventRecord(tg.b, s_g));
         part.t_dispatch.push_back(td);
         part.t_gather.push_back(tg);
     }
-    CK(cudaEventRecord(w.ev_comp[rw], w.s_comp));
+    CK(cudaEventRecord(w.ev_comp[rw], s_g));
     p->stats.dispatch_launches++;
     p->stats.gather_launches++;
     p->stats.units_dispatched += n_units;
@@ -465,7 +494,7 @@ static int run_wave(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry& b
             CK(cudaEventRecord(w.ev_out[half], w.s_out));
             CK(cudaEventRecord(wd, w.s_out));
         } else {
-            CK(cudaEventRecord(wd, w.s_comp));
+            CK(cudaEventRecord(wd, s_g));
         }
         part.wave_done.push_back(wd);
     }
@@ -546,8 +575,14 @@ static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry
         cx.args_full = (const uint8_t*)part.d_args_full;
     }
 
+    // ALU-bound bodies with device-resident output: gather(w) runs on a second stream while the next
+    // wave's dispatch kernel computes; so does every map whose arguments / output live on a peer
+    // GPU (the gather's NVLink stores then overlap the next dispatch's NVLink loads: full duplex).
+    const bool peer_io = (cx.args_dev || cx.out_dev) && part.worker != 0;
+    cx.overlap = cx.full_window && !cx.resilient && (body.overlap_gather || peer_io) &&
+                 !(p->flags & FBR_POOL_NO_OVERLAP) && getenv("FBR_NO_OVERLAP") == nullptr;
     // wave capacity in claim units
-    uint64_t units_cap = std::min<uint64_t>(kRecCapacity, p->ring_bytes / cx.slot_stride);
+    uint64_t units_cap = std::min<uint64_t>(kRecCapacity, (cx.overlap ? p->ring_bytes / 2 : p->ring_bytes) / cx.slot_stride);
     if (cx.host_args) units_cap = std::min<uint64_t>(units_cap, p->ring_bytes / ((uint64_t)unit * d.arg_stride));
     if (!cx.full_window) units_cap = std::min<uint64_t>(units_cap, p->ring_bytes / ((uint64_t)unit * R));
     if (units_cap == 0) return fail(FBR_ENOMEM, "ring_bytes=%llu too small for one claim unit of %u tasks", (unsigned long long)p->ring_bytes, unit);
@@ -830,6 +865,7 @@ int fbr_pool_join(fbr_pool_t* p) {
         CK(cudaSetDevice(w.device));
         CK(cudaStreamSynchronize(w.s_in));
         CK(cudaStreamSynchronize(w.s_comp));
+        CK(cudaStreamSynchronize(w.s_gath));
         CK(cudaStreamSynchronize(w.s_out));
     }
     return FBR_OK;

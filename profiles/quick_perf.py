@@ -20,7 +20,19 @@ def report(tag, st):
 
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
-eng = bench.RawEngine(0, 160 << 20)
+import time
+for flags, tag in ((0, "overlap"), (_abi.FBR_POOL_NO_OVERLAP, "serial")):
+    e2 = bench.RawEngine(0, 320 << 20, flags)
+    o2 = e2.dalloc(bench.PI_TASKS)
+    for _ in range(3):
+        e2.wait(e2.submit("pi_inside_det", bench.PI_TASKS, o2))
+    t0 = time.perf_counter()
+    seqs = [e2.submit("pi_inside_det", bench.PI_TASKS, o2) for _ in range(steps)]
+    cnt = [e2.wait(q)[0] for q in seqs]
+    dt = (time.perf_counter() - t0) / steps
+    print("pi %-8s %.4f ms/step (wall, %d pipelined steps) count %d waves %d" % (tag, dt * 1e3, steps, cnt[-1], e2.stats()["dispatch_launches"] // (steps + 3)), flush=True)
+    e2.dfree(o2); e2.close()
+eng = bench.RawEngine(0, 160 << 20, _abi.FBR_POOL_NO_OVERLAP)
 out = eng.dalloc(bench.PI_TASKS)
 for i in range(steps + 3):
     if i == 3:
