@@ -20,7 +20,7 @@ FBR_RES_BYTES, FBR_RES_BOOL, FBR_RES_I64, FBR_RES_U32, FBR_RES_F64X2, FBR_RES_NO
 # body flags
 FBR_BODY_INDEX_ARG, FBR_BODY_NEEDS_SHARED, FBR_BODY_SUMMABLE = 0x1, 0x2, 0x4
 # pool flags
-FBR_POOL_TIMING, FBR_POOL_NO_OVERLAP = 0x1, 0x2
+FBR_POOL_TIMING, FBR_POOL_OVERLAP = 0x1, 0x2
 # map flags
 FBR_MAP, FBR_STARMAP, FBR_APPLY = 0x0, 0x1, 0x2
 FBR_ARGS_DEVICE, FBR_OUT_DEVICE, FBR_WANT_SUM, FBR_SHUFFLE, FBR_FULL_WINDOW, FBR_SHARED_HANDLE, FBR_RESILIENT, \

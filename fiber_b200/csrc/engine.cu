@@ -77,31 +77,30 @@ struct BodyEntry {
     launch_fn launch;
     const void* kernel;
     int max_ctas_per_sm;   // 0 = as many as fit; streaming read+write bodies run best with few, fat streams
-    bool overlap_gather;   // ALU-bound body: run gather(w) concurrently with dispatch(w+1) (second stream)
 };
 
 static const BodyEntry kBodies[F_COUNT] = {
     {"square_i64", 8, 8, FBR_RES_I64, FBR_BODY_INDEX_ARG | FBR_BODY_SUMMABLE, 4096, launch_thread<SquareI64>,
-     (const void*)dispatch_thread_kernel<SquareI64>, 0, false},
+     (const void*)dispatch_thread_kernel<SquareI64>, 0},
     {"mul2_i64", 16, 8, FBR_RES_I64, FBR_BODY_SUMMABLE, 4096, launch_thread<Mul2I64>,
-     (const void*)dispatch_thread_kernel<Mul2I64>, 0, false},
+     (const void*)dispatch_thread_kernel<Mul2I64>, 0},
     {"square_scale_i64", 16, 8, FBR_RES_I64, FBR_BODY_SUMMABLE, 4096, launch_thread<SquareScaleI64>,
-     (const void*)dispatch_thread_kernel<SquareScaleI64>, 0, false},
+     (const void*)dispatch_thread_kernel<SquareScaleI64>, 0},
     {"identity_i64", 8, 8, FBR_RES_I64, FBR_BODY_INDEX_ARG | FBR_BODY_SUMMABLE, 4096, launch_thread<IdentityI64>,
-     (const void*)dispatch_thread_kernel<IdentityI64>, 0, false},
+     (const void*)dispatch_thread_kernel<IdentityI64>, 0},
     {"pi_inside_det", 8, 1, FBR_RES_BOOL, FBR_BODY_INDEX_ARG | FBR_BODY_SUMMABLE, 4096, launch_thread<PiInsideDet>,
-     (const void*)dispatch_thread_kernel<PiInsideDet>, 0, true},
+     (const void*)dispatch_thread_kernel<PiInsideDet>, 0},
     {"parzen_f32", 8, 16, FBR_RES_F64X2, FBR_BODY_NEEDS_SHARED, 1, launch_parzen<float>,
-     (const void*)dispatch_parzen_kernel<float>, 0, false},
+     (const void*)dispatch_parzen_kernel<float>, 0},
     {"parzen_f64", 8, 16, FBR_RES_F64X2, FBR_BODY_NEEDS_SHARED, 1, launch_parzen<double>,
-     (const void*)dispatch_parzen_kernel<double>, 0, false},
+     (const void*)dispatch_parzen_kernel<double>, 0},
     {"payload_map_4k", 4096, 4096, FBR_RES_BYTES, 0, 32, launch_payload_map, (const void*)dispatch_payload_map_kernel,
-     3 /* measured: 3 CTAs/SM = 6641 GB/s, 8 CTAs/SM = 6296 GB/s on the 8.2 GB wave */, false},
+     3 /* measured: 3 CTAs/SM = 6641 GB/s, 8 CTAs/SM = 6296 GB/s on the 8.2 GB wave */},
     {"payload_checksum_4k", 4096, 4, FBR_RES_U32, FBR_BODY_SUMMABLE, 256, launch_payload_checksum,
-     (const void*)dispatch_payload_checksum_kernel, 0, false},
-    {"sleep_f64", 8, 1, FBR_RES_NONE, 0, 1, launch_thread<SleepF64>, (const void*)dispatch_thread_kernel<SleepF64>, 0, false},
+     (const void*)dispatch_payload_checksum_kernel, 0},
+    {"sleep_f64", 8, 1, FBR_RES_NONE, 0, 1, launch_thread<SleepF64>, (const void*)dispatch_thread_kernel<SleepF64>, 0},
     {"fault_identity_i64", 8, 8, FBR_RES_I64, FBR_BODY_INDEX_ARG | FBR_BODY_SUMMABLE, 2, launch_thread<FaultIdentityI64>,
-     (const void*)dispatch_thread_kernel<FaultIdentityI64>, 0, false},
+     (const void*)dispatch_thread_kernel<FaultIdentityI64>, 0},
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -575,12 +574,12 @@ static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry
         cx.args_full = (const uint8_t*)part.d_args_full;
     }
 
-    // ALU-bound bodies with device-resident output: gather(w) runs on a second stream while the next
-    // wave's dispatch kernel computes; so does every map whose arguments / output live on a peer
-    // GPU (the gather's NVLink stores then overlap the next dispatch's NVLink loads: full duplex).
-    const bool peer_io = (cx.args_dev || cx.out_dev) && part.worker != 0;
-    cx.overlap = cx.full_window && !cx.resilient && (body.overlap_gather || peer_io) &&
-                 !(p->flags & FBR_POOL_NO_OVERLAP) && getenv("FBR_NO_OVERLAP") == nullptr;
+    // Opt-in (FBR_POOL_OVERLAP): gather(w) runs on a second, higher-priority stream while the next
+    // wave's / next map's dispatch kernel computes; the ring is then used in alternating halves.
+    // Measured on the pi map (ALU-bound dispatch + HBM-bound gather, maps pipelined back to back):
+    // 0.3837 vs 0.3876 ms/step -- the gather is only 9 % of the step and the two kernels contend for
+    // SM slots, so it is off by default.
+    cx.overlap = cx.full_window && !cx.resilient && (p->flags & FBR_POOL_OVERLAP) != 0;
     // wave capacity in claim units
     uint64_t units_cap = std::min<uint64_t>(kRecCapacity, (cx.overlap ? p->ring_bytes / 2 : p->ring_bytes) / cx.slot_stride);
     if (cx.host_args) units_cap = std::min<uint64_t>(units_cap, p->ring_bytes / ((uint64_t)unit * d.arg_stride));

@@ -87,8 +87,8 @@ int fbr_body_lookup(const char* name, int* func_id);
  * ring_bytes: size of each device ring arena per worker (result ring, and each half of the
  * argument / ordered-output staging rings); 0 selects the default (256 MiB). */
 #define FBR_POOL_TIMING 0x1u  /* bracket every dispatch/gather launch with CUDA events (stats) */
-#define FBR_POOL_NO_OVERLAP 0x2u /* never run gather(w) concurrently with dispatch(w+1): kernels are timed
-                                   in isolation (roofline measurements) */
+#define FBR_POOL_OVERLAP 0x2u  /* run gather(w) on a second stream concurrently with the next dispatch
+                                   (device-resident results only; ring used in halves) */
 int fbr_pool_create(int n_workers, const int* device_ids, uint64_t ring_bytes, uint32_t flags,
                     fbr_pool_t** pool);
 int fbr_pool_close(fbr_pool_t* pool);

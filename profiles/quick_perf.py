@@ -21,7 +21,7 @@ def report(tag, st):
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 import time
-for flags, tag in ((0, "overlap"), (_abi.FBR_POOL_NO_OVERLAP, "serial")):
+for flags, tag in ((_abi.FBR_POOL_OVERLAP, "overlap"), (0, "serial")):
     e2 = bench.RawEngine(0, 320 << 20, flags)
     o2 = e2.dalloc(bench.PI_TASKS)
     for _ in range(3):
@@ -32,7 +32,7 @@ for flags, tag in ((0, "overlap"), (_abi.FBR_POOL_NO_OVERLAP, "serial")):
     dt = (time.perf_counter() - t0) / steps
     print("pi %-8s %.4f ms/step (wall, %d pipelined steps) count %d waves %d" % (tag, dt * 1e3, steps, cnt[-1], e2.stats()["dispatch_launches"] // (steps + 3)), flush=True)
     e2.dfree(o2); e2.close()
-eng = bench.RawEngine(0, 160 << 20, _abi.FBR_POOL_NO_OVERLAP)
+eng = bench.RawEngine(0, 160 << 20)
 out = eng.dalloc(bench.PI_TASKS)
 for i in range(steps + 3):
     if i == 3:

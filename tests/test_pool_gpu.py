@@ -482,3 +482,38 @@ def test_results_on_device_are_fetched_lazily(golden):
         assert r.sum() == count and np.array_equal(np.asarray(r).view(np.uint8), ref)
     with pytest.raises(ValueError):
         fiber_b200.Pool(1, results="disk")
+
+
+def test_overlapped_gather_stream_is_bit_exact():
+    """FBR_POOL_OVERLAP: gather(w) runs on a second stream against alternating ring halves while the
+    next dispatch computes; results and sums must not change."""
+    import ctypes
+    from oracle import cref
+    from fiber_b200 import registry
+    lib = _abi.load()
+    ids = (ctypes.c_int * 1)(0)
+    h = ctypes.c_void_p()
+    _abi.check(lib.fbr_pool_create(1, ids, 8 << 20, _abi.FBR_POOL_OVERLAP, ctypes.byref(h)))   # small ring: many waves
+    n = 20_000_003
+    dout = ctypes.c_void_p()
+    _abi.check(lib.fbr_device_alloc(h, 0, n, ctypes.byref(dout)))
+    seqs = []
+    for k in range(3):                                  # three maps pipelined back to back
+        d = _abi.MapDesc()
+        d.func_id = registry.spec("pi_inside_det").func_id
+        d.flags = _abi.FBR_OUT_DEVICE | _abi.FBR_WANT_SUM
+        d.n_tasks, d.index_start, d.index_step, d.out = n, 0, 1, dout.value
+        s = ctypes.c_uint64()
+        _abi.check(lib.fbr_map_submit(h, ctypes.byref(d), ctypes.byref(s)))
+        seqs.append(s.value)
+    ref, count = cref.pi_inside_range(0, n)
+    for s in seqs:
+        res = _abi.Result()
+        _abi.check(lib.fbr_result_wait(h, s, -1, ctypes.byref(res)))
+        assert res.sum == count and res.n_waves > 2
+        _abi.check(lib.fbr_result_release(h, s))
+    got = np.empty(n, dtype=np.uint8)
+    _abi.check(lib.fbr_memcpy_d2h(h, 0, got.ctypes.data, dout, n))
+    assert np.array_equal(got, ref)
+    lib.fbr_device_free(h, 0, dout)
+    lib.fbr_pool_destroy(h)
