@@ -328,9 +328,12 @@ static void worker_destroy(Worker& w) {
 // Claim-unit size: near the body's preferred size, a multiple of the API chunksize when the chunk
 // is smaller (so chunk boundaries coincide with unit boundaries), and a multiple of 16/R tasks so
 // every full slot is 16 B aligned on both sides of the gather.
-static uint32_t pick_unit(const BodyEntry& b, uint32_t chunksize, uint64_t n_tasks, int sm_count) {
+static uint32_t pick_unit(const BodyEntry& b, uint32_t chunksize, uint64_t n_tasks, int sm_count, uint64_t ring_bytes) {
     uint32_t pref = b.unit_tasks;
     if (pref == 1) return 1;
+    // a unit's results (and its argument records) must fit the ring arenas
+    const uint64_t per_task = std::max<uint64_t>(std::max(b.result_bytes, b.arg_bytes), 1);
+    while (pref > 1 && (uint64_t)pref * per_task > ring_bytes / 2) pref >>= 1;
     // small maps: shrink the unit so the work still spreads over the SMs
     while (pref > 256 && (uint64_t)pref * (uint64_t)sm_count > n_tasks) pref >>= 1;
     const uint32_t align = b.result_bytes < 16 ? 16u / b.result_bytes : 1u;
@@ -341,6 +344,7 @@ static uint32_t pick_unit(const BodyEntry& b, uint32_t chunksize, uint64_t n_tas
         if (m <= 2 * pref) unit = std::max(m, pref / m * m);
     }
     unit = (uint32_t)round_up(unit, align);
+    while (unit > align && (uint64_t)unit * per_task > ring_bytes) unit -= align;   // chunk-aligned unit too big for the ring
     return unit;
 }
 
@@ -534,7 +538,7 @@ static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry
     cx.full_window = cx.out_dev || cx.resilient || cx.keep_on_device || (d.flags & FBR_FULL_WINDOW);
     cx.host_args = d.arg_stride != 0 && !cx.args_dev && !cx.resilient;
     const uint32_t cs = d.chunksize ? d.chunksize : 32u;
-    cx.unit = pick_unit(body, cs, part.count, w.sm_count);
+    cx.unit = pick_unit(body, cs, part.count, w.sm_count, p->ring_bytes);
     cx.slot_stride = (uint32_t)round_up((uint64_t)cx.unit * cx.R, 16);
     const uint32_t unit = cx.unit, R = cx.R;
 
@@ -971,7 +975,7 @@ int fbr_map_submit(fbr_pool_t* p, const fbr_map_desc_t* d, uint64_t* seq_out) {
     // PUSH round-robin with chunk = block)
     const int nw = (int)p->workers.size();
     const uint32_t cs = d->chunksize ? d->chunksize : 32u;
-    const uint32_t unit = pick_unit(body, cs, (d->n_tasks + nw - 1) / nw, p->workers[0].sm_count);
+    const uint32_t unit = pick_unit(body, cs, (d->n_tasks + nw - 1) / nw, p->workers[0].sm_count, p->ring_bytes);
     const uint64_t units_total = (d->n_tasks + unit - 1) / unit;
     const uint64_t units_per = (units_total + nw - 1) / nw;
     for (int wi = 0; wi < nw && d->n_tasks; ++wi) {
