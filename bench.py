@@ -347,6 +347,33 @@ def fused_peer_map(n_gpus, n_total, steps):
         lib.fbr_pool_destroy(h)
 
 
+
+def inprocess_pool_e2e(n_gpus, steps):
+    """The literal drop-in usage: ONE process, `fiber_b200.Pool(processes=N)` over all N GPUs,
+    `pool.map(is_inside, range(N * 1e8))` -> one pinned ResultArray (each GPU D2Hs its block) + count."""
+    import fiber_b200
+    from examples import workloads as W
+    pool = fiber_b200.Pool(n_gpus)
+    n = n_gpus * PI_TASKS
+    counts = []
+
+    def step():
+        res = pool.map(W.is_inside, range(n))
+        counts.append(res.sum())
+        del res
+    for _ in range(3):
+        step()
+    k = max(3, min(steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(k):
+        step()
+    dt = time.perf_counter() - t0
+    pool.terminate()
+    pool.join()
+    return {"value": n * k / dt, "unit": "tasks/s", "ms_per_step": 1e3 * dt / k, "tasks_per_step": n, "count": counts[-1],
+            "api": "fiber_b200.Pool(%d).map(is_inside_det, range(%d)) in one process" % (n_gpus, n)}
+
+
 def run_multi_gpu(args, dist, dev):
     """BASELINE.json configs[3] and [4] on N GPUs (torch.distributed/NCCL is the exchange plumbing;
     the map itself runs through the C ABI on torch-allocated device buffers):
@@ -425,7 +452,7 @@ def run_multi_gpu(args, dist, dev):
     # (iii) the same root-resident map with scatter and gather FUSED into the kernels: one in-process
     # pool on rank 0 drives all N GPUs; arguments and ordered output live on GPU 0, every worker's
     # dispatch kernel loads its block and its gather kernel stores its units over NVLink peer memory.
-    fused = None
+    fused = inproc = None
     # the other ranks wait on the HOST (store key), not in an NCCL barrier: a spinning NCCL kernel on
     # their GPUs would compete with the peer traffic being measured
     store = td.distributed_c10d._get_default_store()
@@ -434,6 +461,10 @@ def run_multi_gpu(args, dist, dev):
             fused = fused_peer_map(world, n_total, args.steps)
         except Exception as e:          # e.g. the launcher restricted CUDA_VISIBLE_DEVICES per rank
             fused = {"unavailable": "%s: %s" % (type(e).__name__, e)}
+        try:
+            inproc = inprocess_pool_e2e(world, args.steps)
+        except Exception as e:
+            inproc = {"unavailable": "%s: %s" % (type(e).__name__, e)}
         store.set("fbr_fused_done", "1")
     else:
         store.wait(["fbr_fused_done"])
@@ -448,6 +479,7 @@ def run_multi_gpu(args, dist, dev):
                                          "note": "NCCL scatter from rank 0 + map + NCCL gather to rank 0; root link-bound"},
             "fused_peer_memory_root0": fused,
             "parity_spot_check": ok},
+        "inprocess_pool_e2e": inproc,
         "ring_allreduce": {"workload": "all-reduce SUM of 64 Mi fp32 (256 MiB) per rank, %d ranks (BASELINE.json configs[4])" % world,
                            "bit_exact": ar_ok, "algbw_GBps": algbw, "busbw_GBps": busbw, "ms": ar_ms,
                            "nvlink_ref": "measured refs: 725 GB/s all-reduce busbw @1 GiB, 770 GB/s peer copy (B200_PROFILING.md)"},
