@@ -43,6 +43,8 @@ SYMBOLS = [
     "fbr_lane_send", "fbr_lane_recv", "fbr_lane_poll", "fbr_queue_put", "fbr_queue_get", "fbr_queue_stats",
     "fbr_queue_destroy", "fbr_process_start", "fbr_process_poll", "fbr_process_join", "fbr_process_terminate",
     "fbr_process_handled", "fbr_process_destroy",
+    "fbr_express_last_error", "fbr_express_create", "fbr_express_submit", "fbr_express_wait", "fbr_express_stats",
+    "fbr_express_destroy",
 ]
 
 FBR_REC_NONE, FBR_REC_INT, FBR_REC_FLOAT, FBR_REC_BYTES, FBR_REC_STR = range(5)
@@ -160,6 +162,12 @@ def load():
         "fbr_process_terminate": (i32, [vp]),
         "fbr_process_handled": (i32, [vp, P(u64)]),
         "fbr_process_destroy": (i32, [vp]),
+        "fbr_express_last_error": (ctypes.c_char_p, []),
+        "fbr_express_create": (i32, [i32, i32, P(vp)]),
+        "fbr_express_submit": (i32, [vp, i32, ctypes.c_char_p, u32, P(u64)]),
+        "fbr_express_wait": (i32, [vp, u64, vp, P(u32), P(u32), i32]),
+        "fbr_express_stats": (i32, [vp, P(u64), P(u64), P(i32)]),
+        "fbr_express_destroy": (i32, [vp]),
     }
     assert sorted(sig) == sorted(SYMBOLS)
     for name, (res, args) in sig.items():
@@ -175,6 +183,13 @@ def load():
 def check(status):
     if status != FBR_OK:
         raise EngineError(status, load().fbr_last_error().decode("utf-8", "replace"))
+    return status
+
+
+def xcheck(status):
+    """Status check for the express-lane entry points (express.cu keeps its own error string)."""
+    if status != FBR_OK:
+        raise EngineError(status, load().fbr_express_last_error().decode("utf-8", "replace"))
     return status
 
 

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
 SO = os.path.join(LIBDIR, "libfiber_b200.so")
-SOURCES = ["engine.cu", "queues.cu"]
+SOURCES = ["engine.cu", "queues.cu", "express.cu"]
 HEADERS = ["kernels.cuh", "bodies.cuh", os.path.join("..", "..", "include", "fiber_b200.h")]
 
 NVCC_FLAGS = [

@@ -282,11 +282,60 @@ class ApplyResult(MapResult):
         return self._wait(timeout)[0]
 
 
+class _Express:
+    """Owner of one ``fbr_express_t``: the doorbell lane of one device (resident one-warp kernel)."""
+    BODIES = ("square_i64", "mul2_i64", "square_scale_i64", "identity_i64", "pi_inside_det", "sleep_f64")
+
+    def __init__(self, device, idle_us):
+        self.lib = _abi.load()
+        h = ctypes.c_void_p()
+        _abi.xcheck(self.lib.fbr_express_create(device, idle_us, ctypes.byref(h)))
+        self.handle = h
+
+    def stats(self):
+        served, launches, resident = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_int()
+        _abi.xcheck(self.lib.fbr_express_stats(self.handle, ctypes.byref(served), ctypes.byref(launches), ctypes.byref(resident)))
+        return {"served": served.value, "kernel_launches": launches.value, "resident": bool(resident.value)}
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            self.lib.fbr_express_destroy(h)
+
+
+class ExpressResult:
+    """``ApplyResult`` (fiber/pool.py:746-757) of a task sent through the doorbell lane."""
+
+    def __init__(self, pool, express, spec, ticket):
+        self._pool, self._x, self._spec, self._ticket = pool, express, spec, ticket
+        self._done, self._value = False, None
+
+    def get(self, timeout=None):
+        if self._done:
+            return self._value
+        buf = (ctypes.c_uint8 * 48)()
+        nbytes, err = ctypes.c_uint32(), ctypes.c_uint32()
+        rc = self._x.lib.fbr_express_wait(self._x.handle, self._ticket, buf, ctypes.byref(nbytes), ctypes.byref(err),
+                                          -1 if timeout is None else int(timeout * 1000))
+        if rc == _abi.FBR_ETIMEOUT:
+            raise TimeoutError("apply %d not finished" % self._ticket)
+        if rc == _abi.FBR_ETASK:
+            self._done = True
+            res = _abi.Result()
+            res.err_code, res.err_task = err.value, 0
+            MapResult._raise_task_error(self, res)
+        _abi.xcheck(rc)
+        self._value, self._done = self._spec.unpack_result(bytes(buf[: nbytes.value])), True
+        self._pool.recv_tasks += 1
+        return self._value
+
+
 class Pool:
     """B200-native drop-in for ``fiber.Pool`` on the map/starmap/apply path."""
 
     def __init__(self, processes=None, initializer=None, initargs=(), maxtasksperchild=None,
-                 error_handling=False, *, devices=None, ring_bytes=0, timing=False, results="host"):
+                 error_handling=False, *, devices=None, ring_bytes=0, timing=False, results="host", express=True,
+                 express_idle_us=2000):
         self._processes = processes if processes is not None else 1   # fiber/pool.py:894
         if self._processes < 1:
             raise ValueError("Number of processes must be at least 1")
@@ -303,6 +352,9 @@ class Pool:
         if results not in ("host", "device"):
             raise ValueError("results must be 'host' (pinned result segment) or 'device' (stay in HBM, fetched lazily)")
         self._results_on_device = results == "device"
+        self._use_express = bool(express) and not self._error_handling
+        self._express_idle_us = int(express_idle_us)
+        self._express = None
         self._state = RUN
         self._engine = None
         self._worker_handler_started = False
@@ -448,6 +500,16 @@ class Pool:
         self._check_running()
         spec = self._spec_of(func)
         self.lazy_start_workers(func)
+        if self._use_express and spec.name in _Express.BODIES:
+            # one task whose record fits the doorbell lane: no kernel launch / copy on the round trip
+            rec = spec.pack_apply(args, kwds)
+            if self._express is None:
+                self._express = _Express(self._engine.devices[0], self._express_idle_us)
+            ticket = ctypes.c_uint64()
+            _abi.xcheck(self._express.lib.fbr_express_submit(self._express.handle, spec.func_id, rec, len(rec),
+                                                             ctypes.byref(ticket)))
+            self.sent_tasks += 1
+            return ExpressResult(self, self._express, spec, ticket.value)
         return self._submit(func, spec.encode_apply(args, kwds), _abi.FBR_APPLY, 1, cls=ApplyResult, want_sum=False)
 
     def apply(self, func, args=(), kwds={}):
@@ -492,7 +554,10 @@ class Pool:
         self.start_workers()
         s = _abi.Stats()
         _abi.check(self._engine.lib.fbr_pool_stats(self._engine.handle, ctypes.byref(s)))
-        return s.as_dict()
+        d = s.as_dict()
+        if self._express is not None:
+            d["express"] = self._express.stats()
+        return d
 
     def reset_stats(self):
         self.start_workers()

@@ -12,6 +12,7 @@ Encoders turn the Python-level task arguments (what the reference would pickle,
 fiber/pool.py:1181,1297-1301,1112-1113) into fixed-layout argument records.
 """
 import hashlib
+import struct
 
 import numpy as np
 
@@ -132,6 +133,26 @@ class BodySpec:
             raise TypeError("starmap items must be argument tuples, got %r" % (item,))
         return tuple(item), {}
 
+    # ---- single-record fast path (doorbell lane): no NumPy on the round trip ---------------------
+    def pack_apply(self, args, kwds):
+        """One task's argument record as bytes (default: through the array encoder)."""
+        enc = self.encode_apply(args, kwds)
+        return np.ascontiguousarray(enc.args).tobytes()
+
+    def unpack_result(self, raw):
+        k = self.result_kind
+        if k == _abi.FBR_RES_NONE:
+            return None
+        if k == _abi.FBR_RES_BOOL:
+            return raw[0] != 0
+        if k == _abi.FBR_RES_I64:
+            return struct.unpack_from("<q", raw)[0]
+        if k == _abi.FBR_RES_U32:
+            return struct.unpack_from("<I", raw)[0]
+        if k == _abi.FBR_RES_F64X2:
+            return struct.unpack_from("<dd", raw)
+        return list(raw)
+
     # ---- result decoding -----------------------------------------------------------------------
     def result_dtype(self):
         k = self.result_kind
@@ -170,6 +191,14 @@ class BodySpec:
 class _UnaryI64(BodySpec):
     """f(x) with one int argument: square_i64, identity_i64, pi_inside_det, fault_identity_i64."""
 
+    def pack_apply(self, args, kwds):
+        if len(args) != 1 or kwds or type(args[0]) is not int:
+            return super().pack_apply(args, kwds)       # full validation / error messages
+        try:
+            return struct.pack("<q", args[0])
+        except struct.error:
+            raise OverflowError("%s: Python int too large for the int64 task record" % self.name) from None
+
     def _fast_map_ok(self, items):
         return True
 
@@ -201,6 +230,14 @@ class _BinaryI64(BodySpec):
     def __init__(self, info, y_default=None):
         super().__init__(info)
         self.y_default = y_default
+
+    def pack_apply(self, args, kwds):
+        if not kwds and len(args) == 2 and type(args[0]) is int and type(args[1]) is int:
+            try:
+                return struct.pack("<qq", args[0], args[1])
+            except struct.error:
+                raise OverflowError("%s: Python int too large for the int64 task record" % self.name) from None
+        return super().pack_apply(args, kwds)
 
     def _encode(self, items, fast, apply=False):
         rows = []

@@ -253,6 +253,20 @@ int fbr_process_terminate(fbr_process_t* proc);
 int fbr_process_handled(fbr_process_t* proc, uint64_t* handled);
 int fbr_process_destroy(fbr_process_t* proc);
 
+/* ---- express lane: doorbell path for one-task submissions (apply / apply_async) --------------------
+ * A resident one-warp kernel per device polls a pinned, device-mapped request lane, runs the body and
+ * writes the result record into a pinned response lane the host polls: no kernel launch, copy or
+ * event on the round trip (fiber/pool.py:1089-1116 pays a TCP round trip per apply).  The kernel exits
+ * after `idle_timeout_us` without requests and is relaunched on demand.  Bodies whose argument and
+ * result fit 48 bytes: square_i64, mul2_i64, square_scale_i64, identity_i64, pi_inside_det, sleep_f64. */
+typedef struct fbr_express fbr_express_t;
+const char* fbr_express_last_error(void);
+int fbr_express_create(int device_id, int idle_timeout_us, fbr_express_t** x);
+int fbr_express_submit(fbr_express_t* x, int func_id, const void* arg, uint32_t arg_bytes, uint64_t* ticket);
+int fbr_express_wait(fbr_express_t* x, uint64_t ticket, void* result, uint32_t* result_bytes, uint32_t* err, int timeout_ms);
+int fbr_express_stats(fbr_express_t* x, uint64_t* served, uint64_t* launches, int* resident);
+int fbr_express_destroy(fbr_express_t* x);
+
 #ifdef __cplusplus
 }
 #endif

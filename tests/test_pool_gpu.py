@@ -517,3 +517,35 @@ def test_overlapped_gather_stream_is_bit_exact():
     assert np.array_equal(got, ref)
     lib.fbr_device_free(h, 0, dout)
     lib.fbr_pool_destroy(h)
+
+
+def test_express_lane_apply(golden):
+    """apply / apply_async of record-sized bodies go through the doorbell lane (resident kernel,
+    no launch per task) and must behave exactly like the wave path."""
+    import time
+    pool = fiber_b200.Pool(1)
+    slow = fiber_b200.Pool(1, express=False)
+    g = golden("pool_known_answers")
+    assert pool.apply_async(W.f, (42,)).get() == g["apply_async_42"] == slow.apply_async(W.f, (42,)).get()
+    assert pool.apply(W.f, (36,)) == g["apply_36"] and pool.apply(W.fy, (36,), {"y": 2}) == g["apply_kwds_36_y2"]
+    assert pool.apply(W.f2, (7, -6)) == -42 and pool.apply(W.identity, (-5,)) == -5
+    assert pool.apply(W.is_inside, (12345,)) in (True, False) and pool.apply(W.sleep_worker, (0.0001,)) is None
+    assert [pool.apply(W.is_inside, (p,)) for p in range(64)] == [bool(v) for v in golden("pi_inside_det")["head_256"][:64]]
+    with pytest.raises(OverflowError):
+        pool.apply(W.f, (3037000500,))
+    hs = [pool.apply_async(W.f, (i,)) for i in range(3000)]              # more than the lane holds
+    assert [h.get() for h in reversed(hs)][::-1] == [i * i for i in range(3000)]   # out-of-order gets
+    st = pool.stats()["express"]
+    assert st["served"] >= 3070 and st["kernel_launches"] >= 1
+    time.sleep(0.05)                                                      # idle: the resident kernel leaves
+    assert pool.stats()["express"]["resident"] is False
+    assert pool.apply(W.f, (9,)) == 81                                     # and is relaunched on demand
+    assert pool.stats()["express"]["kernel_launches"] >= 2
+    # parzen does not fit a record: it keeps using the wave path on the same pool
+    from oracle import bodies as B
+    xs, px, widths = B.parzen_example_inputs()
+    h, dens = pool.apply(W.parzen_estimation, (xs, px, widths[3]))
+    assert (h, dens) == tuple(float.fromhex(v) for v in golden("parzen_102")["results_hex"][3])
+    for p in (pool, slow):
+        p.terminate()
+        p.join()
