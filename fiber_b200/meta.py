@@ -1,25 +1,24 @@
-"""``fiber_b200.meta`` -- the resource-hint decorator of the reference (fiber/meta.py:16-58).
-
-Same keys (``cpu``, ``memory`` -> stored as ``mem``, ``gpu``), same storage attribute
-``func.__fiber_meta__``; the pool reads it when it starts its workers (fiber/pool.py:1122-1137).
-"""
+"""Resource-hint decorator with the reference's contract (fiber/meta.py:28-58): hints are attached to
+the function as ``__fiber_meta__``; the accepted names are ``cpu``, ``memory`` (stored as ``mem``,
+megabytes) and ``gpu``.  The pool compares this attribute when it starts its workers
+(fiber/pool.py:1122-1137)."""
 
 VALID_META_KEYS = ["cpu", "memory", "gpu"]
+_STORED_AS = {"memory": "mem"}
 
 
 def post_process(metadata):
-    # memory is given in MB and stored under "mem" (fiber/meta.py:19-25)
-    if "memory" in metadata:
-        metadata["mem"] = metadata.pop("memory")
-    return metadata
+    """Rename hint keys to the names they are stored under."""
+    return {_STORED_AS.get(name, name): value for name, value in metadata.items()}
 
 
-def meta(**kwargs):
-    for k in kwargs:
-        assert k in VALID_META_KEYS, "Invalid meta argument \"{}\"".format(k)
+def meta(**hints):
+    unknown = [name for name in hints if name not in VALID_META_KEYS]
+    assert not unknown, "Invalid meta argument \"{}\"".format(unknown[0])
+    stored = post_process(hints)
 
-    def decorator(func):
-        func.__fiber_meta__ = post_process(dict(kwargs))
+    def attach(func):
+        func.__fiber_meta__ = dict(stored)
         return func
 
-    return decorator
+    return attach
