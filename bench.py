@@ -617,7 +617,7 @@ def run_ours(args, dist):
         multi = run_multi_gpu(args, dist, dev)
 
     # ---------------- e2e: the public API with host buffers ---------------------------------------------
-    pool = fiber_b200.Pool(1, devices=[dev], timing=False)
+    pool = fiber_b200.Pool(1, devices=[dev], timing=False, bind_cpu=world > 1)   # N>1: NUMA-local pinned segments
     my_range = range(my_first, my_first + PI_TASKS)
     e2e_counts = []
 
@@ -635,7 +635,8 @@ def run_ours(args, dist):
     e2e_value = world * PI_TASKS * args.steps / t_e2e
     e2e = {"value": e2e_value, "unit": "tasks/s", "ms_per_step": 1e3 * t_e2e / args.steps,
            "h2d_bytes_per_step": se["h2d_bytes"] // args.steps, "d2h_bytes_per_step": se["d2h_bytes"] // args.steps,
-           "api": "fiber_b200.Pool(1).map(is_inside_det, range(1e8)) -> pinned ResultArray + count"}
+           "api": "fiber_b200.Pool(1).map(is_inside_det, range(1e8)) -> pinned ResultArray + count",
+           "cpu_binding": ("%d GPU-local CPUs" % len(pool.bound_cpus)) if pool.bound_cpus else "none"}
     launches_e2e = se["dispatch_launches"] + se["gather_launches"]
 
     # e2e of the 4 KB payload map: records in pinned host memory -> H2D -> map -> D2H (PCIe-bound)

@@ -335,7 +335,7 @@ class Pool:
 
     def __init__(self, processes=None, initializer=None, initargs=(), maxtasksperchild=None,
                  error_handling=False, *, devices=None, ring_bytes=0, timing=False, results="host", express=True,
-                 express_idle_us=2000):
+                 express_idle_us=2000, bind_cpu=False):
         self._processes = processes if processes is not None else 1   # fiber/pool.py:894
         if self._processes < 1:
             raise ValueError("Number of processes must be at least 1")
@@ -355,6 +355,8 @@ class Pool:
         self._use_express = bool(express) and not self._error_handling
         self._express_idle_us = int(express_idle_us)
         self._express = None
+        self._bind_cpu = bool(bind_cpu)      # one process per GPU: keep pinned segments on the GPU's NUMA node
+        self.bound_cpus = []
         self._state = RUN
         self._engine = None
         self._worker_handler_started = False
@@ -379,6 +381,9 @@ class Pool:
             else:
                 # one worker per GPU; more requested processes than GPUs fold onto the GPUs we have
                 devs = list(range(min(self._processes, n.value)))
+            if self._bind_cpu and len(devs) == 1:
+                from .affinity import bind_to_device
+                self.bound_cpus = bind_to_device(devs[0])
             self._engine = _Engine(len(devs), devs, self._ring_bytes, self._timing)
         self._worker_handler_started = True
 
