@@ -58,7 +58,13 @@ typedef void (*launch_fn)(const WaveParams&, int grid, cudaStream_t);
 
 template <class B>
 static void launch_thread(const WaveParams& wp, int grid, cudaStream_t s) {
-    dispatch_thread_kernel<B><<<grid, kThreads, 0, s>>>(wp);
+    if constexpr (B::kIndexArg) {
+        if (wp.arg_stride == 0) {
+            dispatch_thread_kernel<B, true><<<grid, kThreads, 0, s>>>(wp);
+            return;
+        }
+    }
+    dispatch_thread_kernel<B, false><<<grid, kThreads, 0, s>>>(wp);
 }
 static void launch_payload_map(const WaveParams& wp, int grid, cudaStream_t s) {
     dispatch_payload_map_kernel<<<grid, kThreads, 0, s>>>(wp);
@@ -81,15 +87,15 @@ struct BodyEntry {
 
 static const BodyEntry kBodies[F_COUNT] = {
     {"square_i64", 8, 8, FBR_RES_I64, FBR_BODY_INDEX_ARG | FBR_BODY_SUMMABLE, 4096, launch_thread<SquareI64>,
-     (const void*)dispatch_thread_kernel<SquareI64>, 0},
+     (const void*)dispatch_thread_kernel<SquareI64, false>, 0},
     {"mul2_i64", 16, 8, FBR_RES_I64, FBR_BODY_SUMMABLE, 4096, launch_thread<Mul2I64>,
-     (const void*)dispatch_thread_kernel<Mul2I64>, 0},
+     (const void*)dispatch_thread_kernel<Mul2I64, false>, 0},
     {"square_scale_i64", 16, 8, FBR_RES_I64, FBR_BODY_SUMMABLE, 4096, launch_thread<SquareScaleI64>,
-     (const void*)dispatch_thread_kernel<SquareScaleI64>, 0},
+     (const void*)dispatch_thread_kernel<SquareScaleI64, false>, 0},
     {"identity_i64", 8, 8, FBR_RES_I64, FBR_BODY_INDEX_ARG | FBR_BODY_SUMMABLE, 4096, launch_thread<IdentityI64>,
-     (const void*)dispatch_thread_kernel<IdentityI64>, 0},
+     (const void*)dispatch_thread_kernel<IdentityI64, false>, 0},
     {"pi_inside_det", 8, 1, FBR_RES_BOOL, FBR_BODY_INDEX_ARG | FBR_BODY_SUMMABLE, 4096, launch_thread<PiInsideDet>,
-     (const void*)dispatch_thread_kernel<PiInsideDet>, 0},
+     (const void*)dispatch_thread_kernel<PiInsideDet, false>, 0},
     {"parzen_f32", 8, 16, FBR_RES_F64X2, FBR_BODY_NEEDS_SHARED, 1, launch_parzen<float>,
      (const void*)dispatch_parzen_kernel<float>, 0},
     {"parzen_f64", 8, 16, FBR_RES_F64X2, FBR_BODY_NEEDS_SHARED, 1, launch_parzen<double>,
@@ -98,9 +104,9 @@ static const BodyEntry kBodies[F_COUNT] = {
      3 /* measured: 3 CTAs/SM = 6641 GB/s, 8 CTAs/SM = 6296 GB/s on the 8.2 GB wave */},
     {"payload_checksum_4k", 4096, 4, FBR_RES_U32, FBR_BODY_SUMMABLE, 256, launch_payload_checksum,
      (const void*)dispatch_payload_checksum_kernel, 0},
-    {"sleep_f64", 8, 1, FBR_RES_NONE, 0, 1, launch_thread<SleepF64>, (const void*)dispatch_thread_kernel<SleepF64>, 0},
+    {"sleep_f64", 8, 1, FBR_RES_NONE, 0, 1, launch_thread<SleepF64>, (const void*)dispatch_thread_kernel<SleepF64, false>, 0},
     {"fault_identity_i64", 8, 8, FBR_RES_I64, FBR_BODY_INDEX_ARG | FBR_BODY_SUMMABLE, 2, launch_thread<FaultIdentityI64>,
-     (const void*)dispatch_thread_kernel<FaultIdentityI64>, 0},
+     (const void*)dispatch_thread_kernel<FaultIdentityI64, false>, 0},
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -284,10 +290,11 @@ static int worker_init(fbr_pool* p, Worker& w, int device) {
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kBodies[f].kernel, kThreads, 0));
         w.occ[f] = occ > 0 ? occ : 1;
     }
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w.occ_gather, (const void*)gather_ordered_kernel<false>, kThreads, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w.occ_gather, (const void*)gather_ordered_kernel, kThreads, 0));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w.occ_fill, (const void*)payload_fill_kernel, kThreads, 0));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w.occ_gather_rows, (const void*)gather_rows_kernel<true>, kThreads, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w.occ_gather_rows, (const void*)gather_rows_kernel, kThreads, 0));
     if (w.occ_gather_rows < 1) w.occ_gather_rows = 1;
+    CK(cudaFuncSetAttribute(gather_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bulk::kStages * bulk::kChunk)));
     if (w.occ_gather < 1) w.occ_gather = 1;
     if (w.occ_fill < 1) w.occ_fill = 1;
     // no cudaDeviceSynchronize here: it would wait for resident device processes (queues.cu)
@@ -418,6 +425,7 @@ static int run_wave(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry& b
     wp.shared_bytes = d.shared_bytes;
     wp.err_word = &w.d_ctrl[slot].err;
     wp.resilient = cx.resilient ? 1u : 0u;
+    wp.sum = cx.sum_kind ? &w.d_ctrl[slot].sum : nullptr;
     int occ_d = w.occ[st.func_id];
     if (body.max_ctas_per_sm) occ_d = std::min(occ_d, body.max_ctas_per_sm);
     if (ov && occ_d > 1) occ_d -= 1;     // leave SM slots for the concurrently running gather CTAs
@@ -444,10 +452,9 @@ static int run_wave(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry& b
     gp.n_units = n_units;
     gp.slot_stride = cx.slot_stride;
     gp.result_bytes = cx.R;
-    gp.sum_kind = cx.sum_kind;
+    gp.pad = 0;
     gp.out = cx.full_window ? cx.window_base : w.d_out[half];
     gp.win_first = cx.full_window ? part.first : wave_first;
-    gp.sum = &w.d_ctrl[slot].sum;
     gp.ticket_to_reset = wp.ticket;
     gp.lost_count = cx.resilient ? &w.d_ctrl[slot].lost_count : nullptr;
     gp.lost_units = part.d_lost;
@@ -455,12 +462,32 @@ static int run_wave(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry& b
     const uint64_t total_vec = (uint64_t)n_units * (cx.slot_stride >> 4);
     const int grid_g = (int)std::max<uint64_t>(1, std::min<uint64_t>((total_vec + kThreads * 4 - 1) / (kThreads * 4),
                                                                       (uint64_t)w.sm_count * w.occ_gather));
-    // fast path: slots made of whole 4 KB rows and a 16 B aligned output window
-    const bool rows_ok = (cx.slot_stride % 4096 == 0) && (((uintptr_t)gp.out & 15) == 0) &&
-                         (((uint64_t)cx.unit * cx.R) == cx.slot_stride) && getenv("FBR_GATHER_FLAT") == nullptr;
-    if (rows_ok) {
-        uint32_t* gticket = w.d_tickets + kTickets + (wno % kTickets);   // zero at launch, re-armed below
-        // ~128 KB of ring per ticket, but never fewer than ~4 tickets per resident CTA (small waves)
+    // kernel choice for this wave (see kernels.cuh): TMA bulk pipeline, row streaming, or flat
+    const bool aligned = (((uintptr_t)gp.out & 15) == 0) && (((uint64_t)cx.unit * cx.R) == cx.slot_stride);
+    const bool rows_ok = aligned && (cx.slot_stride % 4096 == 0) && getenv("FBR_GATHER_FLAT") == nullptr;
+    const bool bulk_ok = rows_ok && !cx.resilient &&
+                         (cx.slot_stride % bulk::kChunk == 0 || getenv("FBR_BULK_SMALL") != nullptr) &&   // 4 KB slots: rows kernel is faster (37 vs 41 us on the pi wave)
+                         (cx.slot_stride <= bulk::kChunk || cx.slot_stride % bulk::kChunk == 0) &&
+                         !(getenv("FBR_GATHER_BULK") && atoi(getenv("FBR_GATHER_BULK")) == 0);
+    uint32_t* gticket = w.d_tickets + kTickets + (wno % kTickets);   // zero at launch, re-armed below
+    if (bulk_ok) {
+        const uint32_t stage = std::min<uint32_t>(cx.slot_stride, bulk::kChunk);
+        const size_t smem_bytes = (size_t)bulk::kStages * stage;
+        // big chunks: ONE warp per SM saturates HBM (measured 104 % of the copy peak vs 102.5 % with two);
+        // 4 KB chunks need more CTAs to keep enough bytes in flight
+        int per_sm = stage >= bulk::kChunk ? 1 : (int)std::min<size_t>(8, (200u << 10) / smem_bytes);
+        if (const char* e = getenv("FBR_GATHER_OCC")) per_sm = std::max(1, atoi(e));
+        // ~256 KB of ring per ticket (<= 32 slots: one header per lane), >= ~8 tickets per CTA
+        const uint64_t max_ctas = (uint64_t)w.sm_count * per_sm;
+        uint32_t group_slots = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(
+            std::min<uint64_t>(bulk::kGroup, (256u << 10) / cx.slot_stride), n_units / (8 * max_ctas)));
+        if (const char* e = getenv("FBR_BULK_GROUP")) group_slots = std::max(1, std::min(32, atoi(e)));
+        const uint32_t n_groups = (n_units + group_slots - 1) / group_slots;
+        const int grid_b = (int)std::min<uint64_t>(n_groups, max_ctas);
+        gather_bulk_kernel<<<grid_b, 32, smem_bytes, s_g>>>(gp, gticket, stage, group_slots);
+        CK(cudaMemsetAsync(gticket, 0, sizeof(uint32_t), s_g));
+    } else if (rows_ok) {
+        // ~128 KB of ring per ticket, but never fewer than ~4 tickets per resident CTA (small waves);
         // big slots (>= 32 KB): 4 fat streams per SM measured best (100 % of the copy peak vs 99 %)
         int occ_g = cx.slot_stride >= (32u << 10) ? std::min(w.occ_gather_rows, 4) : w.occ_gather_rows;
         if (const char* e = getenv("FBR_GATHER_OCC")) occ_g = std::max(1, std::min(occ_g, atoi(e)));
@@ -468,11 +495,11 @@ static int run_wave(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry& b
         const uint32_t group_slots = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((128u << 10) / cx.slot_stride, n_units / (4 * max_ctas)));
         const uint32_t n_groups = (n_units + group_slots - 1) / group_slots;
         const int grid_r = (int)std::min<uint64_t>(n_groups, max_ctas);
-        if (cx.sum_kind) gather_rows_kernel<true><<<grid_r, kThreads, 0, s_g>>>(gp, gticket, group_slots);
-        else gather_rows_kernel<false><<<grid_r, kThreads, 0, s_g>>>(gp, gticket, group_slots);
+        gather_rows_kernel<<<grid_r, kThreads, 0, s_g>>>(gp, gticket, group_slots);
         CK(cudaMemsetAsync(gticket, 0, sizeof(uint32_t), s_g));
-    } else if (cx.sum_kind) gather_ordered_kernel<true><<<grid_g, kThreads, 0, s_g>>>(gp);
-    else gather_ordered_kernel<false><<<grid_g, kThreads, 0, s_g>>>(gp);
+    } else {
+        gather_ordered_kernel<<<grid_g, kThreads, 0, s_g>>>(gp);
+    }
     CK(cudaGetLastError());
     if (timing) {
         CK(cudaEventRecord(tg.b, s_g));
@@ -621,10 +648,8 @@ static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry
     }
 
     if (d.flags & FBR_WANT_SUM) {
-        if (body.result_kind == FBR_RES_BOOL) cx.sum_kind = kSumBool;
-        else if (body.result_kind == FBR_RES_I64) cx.sum_kind = kSumI64;
-        else if (body.result_kind == FBR_RES_U32) cx.sum_kind = kSumU32;
-        else return fail(FBR_EINVAL, "body %s results cannot be summed", body.name);
+        if (!(body.flags & FBR_BODY_SUMMABLE)) return fail(FBR_EINVAL, "body %s results cannot be summed", body.name);
+        cx.sum_kind = 1;   // the dispatch kernel folds sum(results) while they are in registers
     }
 
     uint64_t done_tasks = 0;
@@ -740,10 +765,13 @@ int fbr_internal_preload(int device) {
     if (cudaSetDevice(device) != cudaSuccess) return FBR_ECUDA;
     cudaFuncAttributes at;
     for (int f = 0; f < F_COUNT; ++f) cudaFuncGetAttributes(&at, kBodies[f].kernel);
-    cudaFuncGetAttributes(&at, (const void*)gather_ordered_kernel<false>);
-    cudaFuncGetAttributes(&at, (const void*)gather_ordered_kernel<true>);
-    cudaFuncGetAttributes(&at, (const void*)gather_rows_kernel<false>);
-    cudaFuncGetAttributes(&at, (const void*)gather_rows_kernel<true>);
+    cudaFuncGetAttributes(&at, (const void*)dispatch_thread_kernel<SquareI64, true>);
+    cudaFuncGetAttributes(&at, (const void*)dispatch_thread_kernel<IdentityI64, true>);
+    cudaFuncGetAttributes(&at, (const void*)dispatch_thread_kernel<PiInsideDet, true>);
+    cudaFuncGetAttributes(&at, (const void*)dispatch_thread_kernel<FaultIdentityI64, true>);
+    cudaFuncGetAttributes(&at, (const void*)gather_ordered_kernel);
+    cudaFuncGetAttributes(&at, (const void*)gather_rows_kernel);
+    cudaFuncGetAttributes(&at, (const void*)gather_bulk_kernel);
     cudaFuncGetAttributes(&at, (const void*)payload_fill_kernel);
     cudaGetLastError();
     return FBR_OK;

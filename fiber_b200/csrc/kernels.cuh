@@ -62,6 +62,7 @@ struct WaveParams {
     uint64_t shared_bytes;
     unsigned long long* err_word;
     uint32_t resilient;         // lost units are re-dispatched by the host (else a fault is an error)
+    long long* sum;             // fold sum(results) here (nullptr: no fold); done where the values are in registers
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -90,11 +91,23 @@ struct TicketClaimer {
     }
 };
 
+// Fold one value per thread into a global accumulator: warp shuffle, then one atomic per warp (no
+// block barrier: a __syncthreads() after the persistent loop made ptxas restructure the whole loop,
+// +15 % instructions on the pi body).
+__device__ __forceinline__ void warp_add(long long v, long long* target) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v != 0) atomicAdd(reinterpret_cast<unsigned long long*>(target), (unsigned long long)v);
+}
+
 // ================================================================================================
 // dispatch: ThreadBody -- one thread per task, V = 16/sizeof(Res) consecutive tasks per thread so
 // each thread emits one 16 B store; a warp writes 512 contiguous bytes of the ring slot.
 // ================================================================================================
-template <class B>
+// kIndex: the task index itself is the argument (range()); a separate instantiation keeps each
+// kernel to one copy of the unrolled body (the two-path version was 45 KB of SASS, beyond the 32 KB
+// instruction cache level).
+template <class B, bool kIndex>
 __global__ void __launch_bounds__(kThreads) dispatch_thread_kernel(const WaveParams wp) {
     using Arg = typename B::Arg;
     using Res = typename B::Res;
@@ -105,13 +118,19 @@ __global__ void __launch_bounds__(kThreads) dispatch_thread_kernel(const WavePar
 
     TicketClaimer tc{wp.ticket, 0u};
     tc.prime();
+    long long acc = 0;            // sum of this thread's results over every unit its CTA completed
     for (;;) {
         if (threadIdx.x == 0) s_fault = 0;
         const uint32_t t = tc.claim(&s_ticket);
-        if (t >= wp.n_units) break;
+        if (t >= wp.n_units) {
+            if (wp.sum != nullptr) warp_add(acc, wp.sum);
+            return;
+        }
         const TaskRecord rec = wp.records[t];
         uint8_t* slot = wp.ring + (size_t)t * wp.slot_stride;
         const uint8_t* uargs = wp.args + rec.arg_off;
+        long long unit_acc = 0;
+        uint32_t unit_acc32 = 0;
 
         for (uint32_t base = threadIdx.x * V; base < rec.count; base += kThreads * V) {
             // results are packed into one 16 B register vector (no local-memory staging)
@@ -119,8 +138,7 @@ __global__ void __launch_bounds__(kThreads) dispatch_thread_kernel(const WavePar
             // implicit range() argument: one multiply per thread, then strength-reduced adds
             // (keeps the integer-multiply pipe for the body: Philox needs 20 IMAD.WIDE per task)
             int64_t a_idx = 0;
-            if constexpr (B::kIndexArg) a_idx = wp.index_start + (int64_t)(rec.first + base) * wp.index_step;
-            const bool index_args = B::kIndexArg && wp.arg_stride == 0;
+            if constexpr (kIndex) a_idx = wp.index_start + (int64_t)(rec.first + base) * wp.index_step;
             const uint64_t gidx0 = wp.index_base + rec.first + base;
 #pragma unroll
             for (int v = 0; v < V; ++v) {
@@ -128,15 +146,12 @@ __global__ void __launch_bounds__(kThreads) dispatch_thread_kernel(const WavePar
                 Res r = Res{};
                 if (i < rec.count) {
                     Arg a;
-                    if constexpr (B::kIndexArg) {
-                        if (index_args) a = (Arg)a_idx;
-                        else a = *reinterpret_cast<const Arg*>(uargs + (size_t)i * wp.arg_stride);
-                    } else {
-                        a = *reinterpret_cast<const Arg*>(uargs + (size_t)i * wp.arg_stride);
-                    }
+                    if constexpr (kIndex) a = (Arg)a_idx;
+                    else a = *reinterpret_cast<const Arg*>(uargs + (size_t)i * wp.arg_stride);
                     r = B::run(a, gidx0 + v, es, rec.attempt);
+                    if constexpr (sizeof(Res) == 8) unit_acc += (long long)r;
                 }
-                if constexpr (B::kIndexArg) a_idx += wp.index_step;
+                if constexpr (kIndex) a_idx += wp.index_step;
                 if constexpr (sizeof(Res) == 1) {
                     pk[v >> 2] |= (uint32_t)(uint8_t)r << ((v & 3) * 8);
                 } else if constexpr (sizeof(Res) == 8) {
@@ -148,6 +163,13 @@ __global__ void __launch_bounds__(kThreads) dispatch_thread_kernel(const WavePar
                     static_assert(sizeof(Res) == 1 || sizeof(Res) == 8, "add a packing rule for this result size");
                 }
             }
+            if constexpr (sizeof(Res) == 1) {     // byte results: fold the packed words with dp4a
+                uint32_t s4 = __dp4a(pk[0], 0x01010101u, 0u);
+                s4 = __dp4a(pk[1], 0x01010101u, s4);
+                s4 = __dp4a(pk[2], 0x01010101u, s4);
+                s4 = __dp4a(pk[3], 0x01010101u, s4);
+                unit_acc32 += s4;
+            }
             uint8_t* dst = slot + (size_t)base * sizeof(Res);
             if (base + V <= rec.count) {
                 st_vec(dst, make_uint4(pk[0], pk[1], pk[2], pk[3]));
@@ -157,6 +179,7 @@ __global__ void __launch_bounds__(kThreads) dispatch_thread_kernel(const WavePar
             }
         }
         __syncthreads();  // s_fault final
+        if (!s_fault) acc += unit_acc + (long long)unit_acc32;   // a lost unit is re-dispatched: never folded twice
         if (threadIdx.x == 0) {
             // A dead worker loses its whole chunk.  ResilientZPool re-queues it; in the plain ZPool
             // the map would hang forever (fiber/pool.py:801-824 has no try/except) -- here it is
@@ -221,6 +244,7 @@ __global__ void __launch_bounds__(kThreads) dispatch_payload_checksum_kernel(con
     TicketClaimer tc{wp.ticket, 0u};
     tc.prime();
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    long long acc = 0;
     for (;;) {
         const uint32_t t = tc.claim(&s_ticket);
         if (t >= wp.n_units) break;
@@ -236,10 +260,11 @@ __global__ void __launch_bounds__(kThreads) dispatch_payload_checksum_kernel(con
             for (int k = 0; k < 8; ++k) s += v[k].x + v[k].y + v[k].z + v[k].w;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0) dst[r] = s;
+            if (lane == 0) { dst[r] = s; acc += (long long)s; }
         }
         if (threadIdx.x == 0) wp.headers[t] = SlotHeader{rec.seq, rec.count, rec.first};
     }
+    if (wp.sum != nullptr) warp_add(acc, wp.sum);
 }
 
 // ================================================================================================
@@ -301,12 +326,20 @@ __global__ void __launch_bounds__(kThreads) dispatch_parzen_kernel(const WavePar
 }
 
 // ================================================================================================
-// gather_ordered: the result ring of one wave is treated as a flat array of 16 B vectors;
-// consecutive threads take consecutive vectors (perfect coalescing on the read side), the slot
-// header tells where the vector lands in the ordered output (out[first*R + ...], placement by
-// index, fiber/pool.py:672).  Slots are full-size except each seq's tail unit, so both sides are
-// 16 B aligned on the fast path; the slow path copies byte-wise.  Lost units are skipped and
-// appended to the lost list for re-dispatch.  Optional epilogue folds sum(results).
+// gather_ordered: result ring -> ordered output by index placement (fiber/pool.py:672).  The ring
+// holds one slot per claim unit in task-record (arrival) order; each slot's header says which
+// tasks it carries.  Three kernels, picked per wave by the host:
+//
+//   gather_bulk_kernel     TMA path (cp.async.bulk, UBLKCP in SASS) for slots of >= 4 KB whose units
+//                          are all valid: one elected thread per CTA pipelines
+//                          ring --bulk load--> shared stage --bulk store--> output; no payload byte
+//                          touches a register.  8.2 GB payload wave: 104 % of the measured HBM copy
+//                          peak with ONE CTA of one warp per SM.
+//   gather_rows_kernel     slots made of whole 4 KB rows, any unit state (lost units skipped and
+//                          listed for re-dispatch, partial tail vector copied byte-wise).
+//   gather_ordered_kernel  flat per-vector kernel for small or unaligned slots.
+//
+// The sum(results) fold lives in the dispatch kernels (where the values are in registers).
 // Algorithmic bytes per task: R read + R written.
 // ================================================================================================
 struct LostUnit { uint64_t first; uint32_t count; uint32_t pad; };
@@ -317,17 +350,14 @@ struct GatherParams {
     uint32_t n_units;
     uint32_t slot_stride;     // bytes, multiple of 16
     uint32_t result_bytes;    // R
-    uint32_t sum_kind;        // 0 none, FBR_RES_BOOL / I64 / U32
+    uint32_t pad;
     uint8_t* out;             // ordered output window
     uint64_t win_first;       // map index of out[0]
-    long long* sum;           // device accumulator (sum_kind != 0)
     uint32_t* ticket_to_reset;  // dispatch ticket of this wave, zeroed for its next use
     uint32_t* lost_count;     // device: number of lost units appended so far (nullable)
     LostUnit* lost_units;     // device: (first, count) of every lost unit, for re-dispatch
     uint32_t lost_capacity;
 };
-
-constexpr uint32_t kSumBool = 1, kSumI64 = 2, kSumU32 = 3;
 
 __device__ __forceinline__ SlotHeader ld_header(const SlotHeader* p) {
     const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
@@ -336,28 +366,32 @@ __device__ __forceinline__ SlotHeader ld_header(const SlotHeader* p) {
     return h;
 }
 
-__device__ __forceinline__ long long sum_vec(const uint4& v, uint32_t kind) {
-    if (kind == kSumBool) {
-        uint32_t a = __dp4a(v.x, 0x01010101u, 0u);
-        a = __dp4a(v.y, 0x01010101u, a);
-        a = __dp4a(v.z, 0x01010101u, a);
-        a = __dp4a(v.w, 0x01010101u, a);
-        return (long long)a;
-    } else if (kind == kSumI64) {
-        return (long long)(((unsigned long long)v.y << 32) | v.x) + (long long)(((unsigned long long)v.w << 32) | v.z);
-    } else {
-        return (long long)v.x + (long long)v.y + (long long)v.z + (long long)v.w;
+__device__ __forceinline__ void copy_tail_bytes(uint8_t* dst, const uint4& data, uint32_t nb) {
+    const uint32_t w[4] = {data.x, data.y, data.z, data.w};
+    for (uint32_t b = 0; b < nb; ++b) dst[b] = (uint8_t)(w[b >> 2] >> ((b & 3) * 8));
+}
+
+// housekeeping shared by the gather kernels: re-arm the wave's dispatch ticket, list lost units
+__device__ __forceinline__ void gather_epilogue(const GatherParams& gp, uint32_t tid, uint32_t nthreads) {
+    if (tid == 0 && gp.ticket_to_reset) *gp.ticket_to_reset = 0u;
+    if (gp.lost_count != nullptr) {
+        for (uint32_t s = tid; s < gp.n_units; s += nthreads) {
+            const SlotHeader h = gp.headers[s];
+            if (h.count & kUnitLost) {
+                const uint32_t k = atomicAdd(gp.lost_count, 1u);
+                if (k < gp.lost_capacity) gp.lost_units[k] = LostUnit{h.first, h.count & ~kUnitLost, 0u};
+            }
+        }
     }
 }
 
-template <bool kSum>
+// ---- flat: one 16 B vector per thread-iteration ------------------------------------------------
 __global__ void __launch_bounds__(kThreads) gather_ordered_kernel(const GatherParams gp) {
     // slot_stride == vps * 16, so ring vector v lives at ring + 16*v: the slot number is only
     // needed to find the header (destination), never for the source address.
     const uint32_t vps = gp.slot_stride >> 4;                   // vectors per slot
     const uint32_t total = gp.n_units * vps;                    // host guarantees < 2^32
     const int sh = (vps & (vps - 1)) == 0 ? (31 - __clz(vps)) : -1;
-    long long acc = 0;
     constexpr int U = 4;
     constexpr uint32_t kTile = kThreads * U;                    // 16 KB of ring per CTA iteration
 
@@ -375,21 +409,6 @@ __global__ void __launch_bounds__(kThreads) gather_ordered_kernel(const GatherPa
         // an unaligned destination takes the byte path as well (flagged in bit 8)
         return nb | (((reinterpret_cast<uintptr_t>(dst) & 15) != 0) ? 0x100u : 0u);
     };
-    auto place = [&](const uint4& data, uint8_t* dst, uint32_t nbf) {
-        if (nbf == 16u) {
-            st_vec(dst, data);
-            if constexpr (kSum) acc += sum_vec(data, gp.sum_kind);
-        } else if (nbf != 0u) {
-            const uint32_t nb = nbf & 0xffu;
-            const uint32_t w[4] = {data.x, data.y, data.z, data.w};
-            for (uint32_t b = 0; b < nb; ++b) dst[b] = (uint8_t)(w[b >> 2] >> ((b & 3) * 8));
-            if constexpr (kSum) {
-                if (gp.sum_kind == kSumBool) { for (uint32_t b = 0; b < nb; ++b) acc += (w[b >> 2] >> ((b & 3) * 8)) & 0xff; }
-                else if (gp.sum_kind == kSumI64) { for (uint32_t b = 0; b + 8 <= nb; b += 8) acc += (long long)(((unsigned long long)w[(b >> 2) + 1] << 32) | w[b >> 2]); }
-                else { for (uint32_t b = 0; b + 4 <= nb; b += 4) acc += w[b >> 2]; }
-            }
-        }
-    };
 
     for (uint32_t base = blockIdx.x * kTile; base < total; base += gridDim.x * kTile) {
         uint4 data[U];
@@ -406,46 +425,17 @@ __global__ void __launch_bounds__(kThreads) gather_ordered_kernel(const GatherPa
             }
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) place(data[u], dst[u], nbf[u]);
-    }
-
-    if constexpr (kSum) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        __shared__ long long s_acc[kThreads / 32];
-        if ((threadIdx.x & 31) == 0) s_acc[threadIdx.x >> 5] = acc;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            long long tot = 0;
-            for (int w = 0; w < kThreads / 32; ++w) tot += s_acc[w];
-            if (tot != 0) atomicAdd(reinterpret_cast<unsigned long long*>(gp.sum), (unsigned long long)tot);
+        for (int u = 0; u < U; ++u) {
+            if (nbf[u] == 16u) st_vec(dst[u], data[u]);
+            else if (nbf[u] != 0u) copy_tail_bytes(dst[u], data[u], nbf[u] & 0xffu);
         }
     }
-    // housekeeping: re-arm the wave's ticket, report lost units for re-dispatch
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        if (gp.ticket_to_reset) *gp.ticket_to_reset = 0u;
-    }
-    if (gp.lost_count != nullptr) {
-        for (uint32_t s = blockIdx.x * kThreads + threadIdx.x; s < gp.n_units; s += gridDim.x * kThreads) {
-            const SlotHeader h = gp.headers[s];
-            if (h.count & kUnitLost) {
-                const uint32_t k = atomicAdd(gp.lost_count, 1u);
-                if (k < gp.lost_capacity) gp.lost_units[k] = LostUnit{h.first, h.count & ~kUnitLost, 0u};
-            }
-        }
-    }
+    gather_epilogue(gp, blockIdx.x * kThreads + threadIdx.x, gridDim.x * kThreads);
 }
 
-// ================================================================================================
-// gather_rows: the fast path of gather_ordered for slots that are a whole number of 4 KB rows
-// (pi: 4096 x 1 B, int64 bodies: 4096 x 8 B, payload map: 32 x 4 KB).  A CTA claims a group of
-// consecutive slots (~128 KB of ring) by ticket and streams it exactly like the payload dispatch
-// kernel: thread j owns the j-th 16 B column of every row, 4 rows in flight, 32 registers so
-// 8 CTAs are resident per SM.  The header of the row's slot gives the destination; lost units are
-// skipped; the partial last vector of a tail unit is copied byte-wise; optional sum epilogue.
-// Measured on the 8.2 GB payload wave: 95.8 % of the HBM copy peak, vs 92 % for the flat kernel.
-// ================================================================================================
-template <bool kSum>
+// ---- rows: a CTA claims ~128 KB of ring by ticket and streams it as 4 KB rows ---------------------
+// Thread j owns the j-th 16 B column of every row, 4 rows in flight.  Measured on the 8.2 GB payload
+// wave: 99.8 % of the HBM copy peak (the flat kernel: 92 %).
 __global__ void __launch_bounds__(kThreads) gather_rows_kernel(const GatherParams gp, uint32_t* ticket, uint32_t group_slots) {
     __shared__ uint32_t s_ticket;
     TicketClaimer tc{ticket, 0u};
@@ -454,7 +444,6 @@ __global__ void __launch_bounds__(kThreads) gather_rows_kernel(const GatherParam
     const uint32_t rps = gp.slot_stride >> 12;                          // 4 KB rows per slot
     const int sh = (rps & (rps - 1)) == 0 ? (31 - __clz(rps)) : -1;
     const uint32_t n_groups = (gp.n_units + group_slots - 1) / group_slots;
-    long long acc = 0;
 
     auto place = [&](const uint4& data, uint32_t slot, uint32_t row_in_slot) {
         const SlotHeader h = ld_header(gp.headers + slot);
@@ -462,19 +451,8 @@ __global__ void __launch_bounds__(kThreads) gather_rows_kernel(const GatherParam
         const uint64_t off = ((uint64_t)row_in_slot << 12) + threadIdx.x * 16;
         if ((h.count & kUnitLost) || off >= valid) return;
         uint8_t* dst = gp.out + (h.first - gp.win_first) * gp.result_bytes + off;
-        if (off + 16 <= valid) {
-            st_vec(dst, data);
-            if constexpr (kSum) acc += sum_vec(data, gp.sum_kind);
-        } else {
-            const uint32_t nb = (uint32_t)(valid - off);
-            const uint32_t w[4] = {data.x, data.y, data.z, data.w};
-            for (uint32_t b = 0; b < nb; ++b) dst[b] = (uint8_t)(w[b >> 2] >> ((b & 3) * 8));
-            if constexpr (kSum) {
-                if (gp.sum_kind == kSumBool) { for (uint32_t b = 0; b < nb; ++b) acc += (w[b >> 2] >> ((b & 3) * 8)) & 0xff; }
-                else if (gp.sum_kind == kSumI64) { for (uint32_t b = 0; b + 8 <= nb; b += 8) acc += (long long)(((unsigned long long)w[(b >> 2) + 1] << 32) | w[b >> 2]); }
-                else { for (uint32_t b = 0; b + 4 <= nb; b += 4) acc += w[b >> 2]; }
-            }
-        }
+        if (off + 16 <= valid) st_vec(dst, data);
+        else copy_tail_bytes(dst, data, (uint32_t)(valid - off));
     };
 
     for (;;) {
@@ -502,29 +480,117 @@ __global__ void __launch_bounds__(kThreads) gather_rows_kernel(const GatherParam
             place(v, slot0 + s, r - s * rps);
         }
     }
+    gather_epilogue(gp, blockIdx.x * kThreads + threadIdx.x, gridDim.x * kThreads);
+}
 
-    if constexpr (kSum) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        __shared__ long long s_acc[kThreads / 32];
-        if ((threadIdx.x & 31) == 0) s_acc[threadIdx.x >> 5] = acc;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            long long tot = 0;
-            for (int w = 0; w < kThreads / 32; ++w) tot += s_acc[w];
-            if (tot != 0) atomicAdd(reinterpret_cast<unsigned long long*>(gp.sum), (unsigned long long)tot);
-        }
+// ---- bulk: TMA pipeline -------------------------------------------------------------------------------
+namespace bulk {
+constexpr uint32_t kChunk = 16384;     // bytes per bulk copy (a slot smaller than this is one chunk)
+constexpr int kStages = 6;             // 96 KB of shared memory per CTA
+constexpr int kLag = 4;                // loads run this many chunks ahead of their store
+constexpr uint32_t kGroup = 32;        // slots per ticket: their headers are prefetched by the 32 lanes
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+}  // namespace bulk
+
+// Requirements checked by the host: slot_stride % 16 == 0 and >= 4 KB, slot_stride <= kChunk or a
+// multiple of kChunk, R % 16 == 0 or every unit full, output window 16 B aligned, no lost units.
+__global__ void __launch_bounds__(32) gather_bulk_kernel(const GatherParams gp, uint32_t* ticket, uint32_t stage_stride,
+                                                         uint32_t group_slots /* <= kGroup */) {
+    using namespace bulk;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t full[kStages];
+    __shared__ SlotHeader s_hdr[kGroup];
+    __shared__ uint32_t s_group;
+    const uint32_t lane = threadIdx.x;
+    if (lane == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0 && gp.ticket_to_reset) *gp.ticket_to_reset = 0u;
-    if (gp.lost_count != nullptr) {
-        for (uint32_t s = blockIdx.x * kThreads + threadIdx.x; s < gp.n_units; s += gridDim.x * kThreads) {
-            const SlotHeader h = gp.headers[s];
-            if (h.count & kUnitLost) {
-                const uint32_t k = atomicAdd(gp.lost_count, 1u);
-                if (k < gp.lost_capacity) gp.lost_units[k] = LostUnit{h.first, h.count & ~kUnitLost, 0u};
+    __syncwarp();
+
+    const uint32_t chunk = gp.slot_stride < kChunk ? gp.slot_stride : kChunk;
+    const uint32_t n_groups = (gp.n_units + group_slots - 1) / group_slots;
+    uint32_t it = 0, st = 0;                             // chunks loaded / stored so far (lane 0)
+    uint8_t* pend_dst[kStages];
+    uint32_t pend_bytes[kStages];
+
+    auto store_one = [&]() {
+        const int sg = st % kStages;
+        mbar_wait(&full[sg], (st / kStages) & 1);
+        bulk_store(pend_dst[sg], smem + (size_t)sg * stage_stride, pend_bytes[sg]);
+        ++st;
+    };
+
+    for (;;) {
+        if (lane == 0) s_group = atomicAdd(ticket, 1u);
+        __syncwarp();
+        const uint32_t g = s_group;
+        if (g >= n_groups) break;
+        const uint32_t slot0 = g * group_slots;
+        const uint32_t nslots = min(group_slots, gp.n_units - slot0);
+        if (lane < nslots) s_hdr[lane] = ld_header(gp.headers + slot0 + lane);   // one coalesced 512 B read
+        __syncwarp();
+        if (lane == 0) {
+            for (uint32_t s = 0; s < nslots; ++s) {
+                const SlotHeader h = s_hdr[s];
+                const uint32_t valid = (h.count & ~kUnitLost) * gp.result_bytes;   // < 4 GiB by construction
+                const uint8_t* src = gp.ring + (size_t)(slot0 + s) * gp.slot_stride;
+                uint8_t* dst = gp.out + (h.first - gp.win_first) * gp.result_bytes;
+                // a tail unit whose byte count is not a multiple of 16: the last <16 bytes go by hand
+                const uint32_t valid16 = valid & ~15u;
+                for (uint32_t b = valid16; b < valid; ++b) dst[b] = src[b];
+                for (uint32_t off = 0; off < valid16; off += chunk) {
+                    const uint32_t bytes = min(chunk, valid16 - off);
+                    const int sg = it % kStages;
+                    // the stage was last used by chunk it-kStages, whose store was issued at least
+                    // kStages-kLag-1 groups ago: wait until it has finished reading shared memory
+                    if (it >= (uint32_t)kStages) bulk_wait_read<kStages - kLag - 1>();
+                    pend_dst[sg] = dst + off;
+                    pend_bytes[sg] = bytes;
+                    mbar_expect_tx(&full[sg], bytes);
+                    bulk_load(smem + (size_t)sg * stage_stride, src + off, bytes, &full[sg]);
+                    ++it;
+                    while (it - st > (uint32_t)kLag) store_one();
+                }
             }
         }
+        __syncwarp();
     }
+    if (lane == 0) {
+        while (st < it) store_one();
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    gather_epilogue(gp, blockIdx.x * 32 + lane, gridDim.x * 32);
 }
 
 // ================================================================================================
