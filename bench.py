@@ -541,7 +541,7 @@ def run_ours(args, dist):
     roofline = {"kernel": "gather_ordered_kernel<sum>", "bound": "hbm",
                 "achieved": gather_bytes / (gather_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": gather_bytes / (gather_ms * 1e-3) / 1e9 / hbm_peak,
-                "traffic": traffic_of("gather_rows_kernel<1>@prof_pi"), "traffic_source": traffic_src, "peak_source": peak_src,
+                "traffic": traffic_of("gather_rows_kernel@prof_pi"), "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": gather_bytes, "avg_launch_ms": gather_ms,
                 "note": "2*R*N bytes (R=1 B) per launch; the ring was just written by the dispatch kernel so part of the reads can hit L2"}
     # Philox4x32-10 + f64 compare: ~20 IMAD.WIDE-class multiplies + ~60 ALU ops per task; the bound
@@ -600,11 +600,11 @@ def run_ours(args, dist):
                                   "frac": d_bytes / (d_ms * 1e-3) / 1e9 / hbm_peak, "avg_launch_ms": d_ms,
                                   "algorithmic_bytes_per_launch": d_bytes,
                                   "traffic": traffic_of("dispatch_payload_map_kernel@prof_payload")},
-            "roofline_gather": {"kernel": "gather_rows_kernel (gather_ordered fast path)", "bound": "hbm",
+            "roofline_gather": {"kernel": "gather_bulk_kernel (gather_ordered, TMA cp.async.bulk path)", "bound": "hbm",
                                 "achieved": g_bytes / (g_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                 "frac": g_bytes / (g_ms * 1e-3) / 1e9 / hbm_peak, "avg_launch_ms": g_ms,
                                 "algorithmic_bytes_per_launch": g_bytes,
-                                "traffic": traffic_of("gather_rows_kernel<0>@prof_payload")},
+                                "traffic": traffic_of("gather_bulk_kernel@prof_payload")},
             "parity_spot_check": ok,
         }
         eng.dfree(in_dev)
