@@ -538,7 +538,7 @@ def run_ours(args, dist):
     gather_ms = st["gather_ms"] / max(1, st["gather_launches"])
     dispatch_ms = st["dispatch_ms"] / max(1, st["dispatch_launches"])
     gather_bytes = st["gather_bytes"] / max(1, st["gather_launches"])
-    roofline = {"kernel": "gather_ordered_kernel<sum>", "bound": "hbm",
+    roofline = {"kernel": "gather_rows_kernel (gather_ordered, 4 KB-row path)", "bound": "hbm",
                 "achieved": gather_bytes / (gather_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": gather_bytes / (gather_ms * 1e-3) / 1e9 / hbm_peak,
                 "traffic": traffic_of("gather_rows_kernel@prof_pi"), "traffic_source": traffic_src, "peak_source": peak_src,
@@ -548,11 +548,14 @@ def run_ours(args, dist):
     # is the SM integer pipes, not HBM (1 B written per task).
     sm_clock = float(peaks.get("sm_max_mhz", 1965.0)) * 1e6
     int_peak = 148 * 128 * sm_clock / 1e12          # lane-ops/s, all SMs, 128 lanes/clk
-    roofline_dispatch = {"kernel": "dispatch_thread_kernel<PiInsideDet>", "bound": "alu",
+    roofline_dispatch = {"kernel": "dispatch_thread_kernel<PiInsideDet, index args> (+ sum fold)", "bound": "alu",
                          "avg_launch_ms": dispatch_ms, "tasks_per_s": PI_TASKS / (dispatch_ms * 1e-3),
                          "hbm_gbs": PI_TASKS * 1 / (dispatch_ms * 1e-3) / 1e9,
-                         "note": "integer/FP64-bound: ~%.0f lane-ops/task at a %.1f Tlane-op/s issue peak" %
-                                 (int_peak * 1e12 * dispatch_ms * 1e-3 / PI_TASKS, int_peak)}
+                         "imad_wide_per_task": 21,
+                         "fmaheavy_frac_ncu": 0.736,
+                         "note": "bound by the integer-multiply pipe: Philox4x32-10 needs 20 IMAD.WIDE.U32 per task (+1 for the "
+                                 "index), ~4 fmaheavy cycles each; ncu (profiles/r01_ncu_kernels.csv) shows fmaheavy 73.6 % "
+                                 "active, dram 1.5 %"}
     eng.dfree(out_dev)
 
     # ---------------- secondary: 4 KB payload map, device resident ----------------------------------
