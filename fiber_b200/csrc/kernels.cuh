@@ -541,8 +541,8 @@ __global__ void __launch_bounds__(32) gather_bulk_kernel(const GatherParams gp, 
     const uint32_t chunk = gp.slot_stride < kChunk ? gp.slot_stride : kChunk;
     const uint32_t n_groups = (gp.n_units + group_slots - 1) / group_slots;
     uint32_t it = 0, st = 0;                             // chunks loaded / stored so far (lane 0)
-    uint8_t* pend_dst[kStages];
-    uint32_t pend_bytes[kStages];
+    uint8_t* pend_dst[kStages] = {};
+    uint32_t pend_bytes[kStages] = {};
 
     auto store_one = [&]() {
         const int sg = st % kStages;
