@@ -188,3 +188,25 @@ def test_pool_argument_validation_without_device():
         p.starmap(W.f, [(1,)])
     p.join()
     assert fiber_b200.active_children() == []
+
+
+def test_affinity_helpers_degrade_gracefully():
+    """No NVML / no GPU: device_cpus is empty and bind_to_device leaves the process untouched."""
+    import os
+    from fiber_b200 import affinity
+    before = os.sched_getaffinity(0)
+    cpus = affinity.device_cpus(0)
+    assert isinstance(cpus, list)
+    if not cpus:
+        assert affinity.bind_to_device(0) == [] and os.sched_getaffinity(0) == before
+    p = fiber_b200.Pool(1, bind_cpu=True, results="device", express=False)
+    assert p.bound_cpus == [] and p._results_on_device and not p._use_express
+
+
+def test_express_and_queue_symbols_need_a_gpu_to_start():
+    lib = _abi.load()
+    if _gpu_present():
+        pytest.skip("checks the no-GPU failure mode")
+    x = ctypes.c_void_p()
+    assert lib.fbr_express_create(0, 0, ctypes.byref(x)) == _abi.FBR_ENODEV
+    assert b"no CPU fallback" in lib.fbr_express_last_error()
