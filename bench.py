@@ -598,11 +598,11 @@ def run_ours(args, dist):
         payload = {
             "workload": "synthetic 4 KB-payload map, %d tasks per GPU, inputs+outputs resident in HBM (4.1 GB each, >> L2)" % PAYLOAD_TASKS,
             "value": world * PAYLOAD_TASKS * args.steps / t_pl, "unit": "tasks/s", "ms_per_step": 1e3 * t_pl / args.steps,
-            "roofline_dispatch": {"kernel": "dispatch_payload_map_kernel", "bound": "hbm",
+            "roofline_dispatch": {"kernel": "dispatch_payload_map_tma_kernel (TMA-staged, warp-specialised)", "bound": "hbm",
                                   "achieved": d_bytes / (d_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                   "frac": d_bytes / (d_ms * 1e-3) / 1e9 / hbm_peak, "avg_launch_ms": d_ms,
                                   "algorithmic_bytes_per_launch": d_bytes,
-                                  "traffic": traffic_of("dispatch_payload_map_kernel@prof_payload")},
+                                  "traffic": traffic_of("dispatch_payload_map_tma_kernel@prof_payload")},
             "roofline_gather": {"kernel": "gather_bulk_kernel (gather_ordered, TMA cp.async.bulk path)", "bound": "hbm",
                                 "achieved": g_bytes / (g_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                 "frac": g_bytes / (g_ms * 1e-3) / 1e9 / hbm_peak, "avg_launch_ms": g_ms,

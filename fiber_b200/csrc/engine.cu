@@ -70,6 +70,19 @@ static void launch_thread(const WaveParams& wp, int grid, cudaStream_t s) {
     dispatch_thread_kernel<B, false><<<grid, kThreads, 0, s>>>(wp);
 }
 static void launch_payload_map(const WaveParams& wp, int grid, cudaStream_t s) {
+    // contiguous records: TMA-staged, warp-specialised kernel (2 CTAs of 5 warps per SM); strided
+    // records (arg_stride > 4096) keep the register-streaming kernel
+    static const bool use_tma = !(getenv("FBR_DISPATCH_TMA") && atoi(getenv("FBR_DISPATCH_TMA")) == 0);
+    if (use_tma && wp.arg_stride == kPayloadBytes) {
+        int sm = 148, dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+        int per_sm = 2;
+        if (const char* e = getenv("FBR_DISPATCH_OCC")) per_sm = std::max(1, std::min(2, atoi(e)));
+        const int g = (int)std::min<uint32_t>(wp.n_units, (uint32_t)(sm * per_sm));
+        dispatch_payload_map_tma_kernel<<<g, 160, tma_map::kSmemBytes, s>>>(wp);
+        return;
+    }
     dispatch_payload_map_kernel<<<grid, kThreads, 0, s>>>(wp);
 }
 static void launch_payload_checksum(const WaveParams& wp, int grid, cudaStream_t s) {
@@ -367,6 +380,7 @@ static int worker_init(fbr_pool* p, Worker& w, int device) {
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w.occ_gather_rows, (const void*)gather_rows_kernel, kThreads, 0));
     if (w.occ_gather_rows < 1) w.occ_gather_rows = 1;
     CK(cudaFuncSetAttribute(gather_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bulk::kStages * bulk::kChunk)));
+    CK(cudaFuncSetAttribute(dispatch_payload_map_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_map::kSmemBytes));
     if (w.occ_gather < 1) w.occ_gather = 1;
     if (w.occ_fill < 1) w.occ_fill = 1;
     // no cudaDeviceSynchronize here: it would wait for resident device processes (queues.cu)
@@ -844,6 +858,7 @@ int fbr_internal_preload(int device) {
     cudaFuncGetAttributes(&at, (const void*)gather_ordered_kernel);
     cudaFuncGetAttributes(&at, (const void*)gather_rows_kernel);
     cudaFuncGetAttributes(&at, (const void*)gather_bulk_kernel);
+    cudaFuncGetAttributes(&at, (const void*)dispatch_payload_map_tma_kernel);
     cudaFuncGetAttributes(&at, (const void*)payload_fill_kernel);
     cudaGetLastError();
     return FBR_OK;

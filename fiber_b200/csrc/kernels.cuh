@@ -594,6 +594,106 @@ __global__ void __launch_bounds__(32) gather_bulk_kernel(const GatherParams gp, 
 }
 
 // ================================================================================================
+// dispatch: payload_map_4k, TMA-staged (warp-specialised).  Same contract as
+// dispatch_payload_map_kernel, for contiguous argument records (arg_stride == 4096):
+//   warp 0 (one elected lane)  claims units by ticket, writes their slot headers, and bulk-loads the
+//                              records in 16 KB chunks into shared-memory IN stages (mbarrier
+//                              complete_tx); it waits on the stage's EMPTY barrier before reuse;
+//   warps 1-4 (128 threads)    wait for a FULL stage, read it (LDS.128), apply out = in*K + t and
+//                              write an OUT stage (STS.128); after a proxy fence + named barrier one
+//                              of them bulk-stores the OUT stage into the result ring.
+// Payload bytes cross registers only between two shared-memory stages; global traffic is TMA only.
+// ================================================================================================
+namespace tma_map {
+constexpr int kInStages = 3, kOutStages = 2;
+constexpr uint32_t kMapChunk = 16384;
+constexpr int kConsumers = 128;
+struct ChunkDesc { uint8_t* dst; uint32_t bytes; uint32_t tbase; };
+constexpr size_t kSmemBytes = (size_t)(kInStages + kOutStages) * kMapChunk;
+}  // namespace tma_map
+
+__global__ void __launch_bounds__(160) dispatch_payload_map_tma_kernel(const WaveParams wp) {
+    using namespace bulk;
+    using namespace tma_map;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t full[kInStages], empty[kInStages];
+    __shared__ ChunkDesc desc[kInStages];
+    uint8_t* in_stage = smem;
+    uint8_t* out_stage = smem + (size_t)kInStages * kMapChunk;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kInStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kConsumers); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        if (lane != 0) return;
+        // ---------------- producer ----------------
+        uint32_t seq = 0;
+        auto acquire_stage = [&]() -> int {
+            const int sg = seq % kInStages;
+            mbar_wait(&empty[sg], ((seq / kInStages) & 1) ^ 1);   // fresh barrier: passes immediately
+            return sg;
+        };
+        for (;;) {
+            const uint32_t t = atomicAdd(wp.ticket, 1u);
+            if (t >= wp.n_units) break;
+            const TaskRecord rec = wp.records[t];
+            wp.headers[t] = SlotHeader{rec.seq, rec.count, rec.first};
+            const uint8_t* src = wp.args + rec.arg_off;
+            uint8_t* dst = wp.ring + (size_t)t * wp.slot_stride;
+            const uint32_t total = rec.count * kPayloadBytes;
+            const uint32_t tbase = (uint32_t)(wp.index_base + rec.first);
+            for (uint32_t off = 0; off < total; off += kMapChunk) {
+                const uint32_t bytes = min(kMapChunk, total - off);
+                const int sg = acquire_stage();
+                desc[sg] = ChunkDesc{dst + off, bytes, tbase + off / kPayloadBytes};
+                mbar_expect_tx(&full[sg], bytes);
+                bulk_load(in_stage + (size_t)sg * kMapChunk, src + off, bytes, &full[sg]);
+                ++seq;
+            }
+        }
+        const int sg = acquire_stage();                 // end marker
+        desc[sg] = ChunkDesc{nullptr, 0u, 0u};
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full[sg])) : "memory");
+        return;
+    }
+
+    // ---------------- consumers (threads 32..159) ----------------
+    const uint32_t ct = threadIdx.x - 32;               // 0..127
+    for (uint32_t seq = 0;; ++seq) {
+        const int sg = seq % kInStages, og = seq % kOutStages;
+        mbar_wait(&full[sg], (seq / kInStages) & 1);
+        const ChunkDesc d = desc[sg];
+        if (d.bytes == 0) break;
+        // the bulk store that last read OUT stage `og` (chunk seq-kOutStages) must be done with it
+        if (ct == 0 && seq >= (uint32_t)kOutStages) bulk_wait_read<kOutStages - 1>();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const uint8_t* in = in_stage + (size_t)sg * kMapChunk;
+        uint8_t* out = out_stage + (size_t)og * kMapChunk;
+        const uint32_t nvec = d.bytes >> 4;
+#pragma unroll
+        for (uint32_t k = 0; k < kMapChunk / 16 / kConsumers; ++k) {
+            const uint32_t v = ct + k * kConsumers;
+            if (v < nvec) {
+                uint4 x = *reinterpret_cast<const uint4*>(in + ((size_t)v << 4));
+                const uint32_t tt = d.tbase + (v >> 8);   // 256 vectors per 4 KB record
+                x.x = x.x * kPayloadMul + tt; x.y = x.y * kPayloadMul + tt;
+                x.z = x.z * kPayloadMul + tt; x.w = x.w * kPayloadMul + tt;
+                *reinterpret_cast<uint4*>(out + ((size_t)v << 4)) = x;
+            }
+        }
+        // IN stage consumed; make the generic-proxy writes to the OUT stage visible to the async proxy
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[sg])) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (ct == 0) bulk_store(d.dst, out, d.bytes);
+    }
+    if (ct == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// ================================================================================================
 // payload_fill: w[t][j] = low32(splitmix64(SEED ^ (t*1024 + j))); each thread emits 16 B.
 // ================================================================================================
 __global__ void __launch_bounds__(kThreads) payload_fill_kernel(uint4* out, uint64_t t0, uint64_t n_vec) {
