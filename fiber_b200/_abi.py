@@ -34,7 +34,7 @@ SYMBOLS = [
     "fbr_body_count", "fbr_body_info", "fbr_body_lookup",
     "fbr_pool_create", "fbr_pool_close", "fbr_pool_terminate", "fbr_pool_join", "fbr_pool_destroy",
     "fbr_pool_n_workers", "fbr_pool_worker_device",
-    "fbr_map_submit", "fbr_shared_put", "fbr_shared_drop",
+    "fbr_map_submit", "fbr_shared_put", "fbr_shared_drop", "fbr_plan_query",
     "fbr_result_wait", "fbr_result_poll", "fbr_result_data", "fbr_result_fetch", "fbr_result_release",
     "fbr_host_alloc", "fbr_host_free", "fbr_device_alloc", "fbr_device_free",
     "fbr_memcpy_h2d", "fbr_memcpy_d2h", "fbr_payload_fill_device",
@@ -67,6 +67,11 @@ class MapDesc(ctypes.Structure):
                 ("index_start", ctypes.c_int64), ("index_step", ctypes.c_int64),
                 ("shared", ctypes.c_void_p), ("shared_bytes", ctypes.c_uint64), ("out", ctypes.c_void_p),
                 ("task_index_base", ctypes.c_uint64), ("shuffle_seed", ctypes.c_uint64)]
+
+
+class Plan(ctypes.Structure):
+    _fields_ = [("unit_tasks", ctypes.c_uint32), ("slot_stride", ctypes.c_uint32), ("n_units", ctypes.c_uint64),
+                ("block_first", ctypes.c_uint64), ("block_count", ctypes.c_uint64)]
 
 
 class Result(ctypes.Structure):
@@ -131,6 +136,7 @@ def load():
         "fbr_map_submit": (i32, [vp, P(MapDesc), P(u64)]),
         "fbr_shared_put": (i32, [vp, vp, u64, P(u64)]),
         "fbr_shared_drop": (i32, [vp, u64]),
+        "fbr_plan_query": (i32, [i32, u64, u32, u64, i32, i32, i32, P(Plan)]),
         "fbr_result_wait": (i32, [vp, u64, i32, P(Result)]),
         "fbr_result_poll": (i32, [vp, u64, P(u64)]),
         "fbr_result_data": (i32, [vp, u64, P(vp)]),

@@ -905,6 +905,28 @@ int fbr_body_lookup(const char* name, int* func_id) {
     return fail(FBR_ENOENT, "no device body named '%s' is compiled into libfiber_b200", name);
 }
 
+int fbr_plan_query(int func_id, uint64_t n_tasks, uint32_t chunksize, uint64_t ring_bytes, int n_workers,
+                   int worker, int sm_count, fbr_plan_t* plan) {
+    if (!plan || func_id < 0 || func_id >= F_COUNT || n_workers < 1 || worker < 0 || worker >= n_workers)
+        return fail(FBR_EINVAL, "bad arguments");
+    const BodyEntry& body = kBodies[func_id];
+    const uint64_t ring = round_up(ring_bytes ? ring_bytes : (256ull << 20), 4096);
+    const uint32_t cs = chunksize ? chunksize : 32u;
+    if (sm_count <= 0) sm_count = 148;
+    // the same two steps fbr_map_submit takes: blocks on the map-level unit, then the block's own unit
+    const uint32_t unit = pick_unit(body, cs, (n_tasks + n_workers - 1) / n_workers, sm_count, ring);
+    const uint64_t units_total = (n_tasks + unit - 1) / unit;
+    const uint64_t units_per = (units_total + n_workers - 1) / n_workers;
+    const uint64_t b0 = std::min<uint64_t>(n_tasks, (uint64_t)worker * units_per * unit);
+    const uint64_t b1 = std::min<uint64_t>(n_tasks, (uint64_t)(worker + 1) * units_per * unit);
+    plan->block_first = b0;
+    plan->block_count = b1 - b0;
+    plan->unit_tasks = pick_unit(body, cs, b1 - b0, sm_count, ring);
+    plan->slot_stride = (uint32_t)round_up((uint64_t)plan->unit_tasks * body.result_bytes, 16);
+    plan->n_units = plan->block_count ? (plan->block_count + plan->unit_tasks - 1) / plan->unit_tasks : 0;
+    return FBR_OK;
+}
+
 int fbr_pool_create(int n_workers, const int* device_ids, uint64_t ring_bytes, uint32_t flags, fbr_pool_t** out) {
     if (!out || n_workers <= 0) return fail(FBR_EINVAL, "bad arguments");
     int ndev = 0;

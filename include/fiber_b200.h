@@ -149,6 +149,20 @@ int fbr_map_submit(fbr_pool_t* pool, const fbr_map_desc_t* desc, uint64_t* seq);
 int fbr_shared_put(fbr_pool_t* pool, const void* host, uint64_t bytes, uint64_t* handle);
 int fbr_shared_drop(fbr_pool_t* pool, uint64_t handle);
 
+/* Host-side planning of a map, without touching a device (pure function of its arguments): the claim
+ * unit fbr_map_submit would pick, the resulting ring slot stride, and worker w's task block.  Lets
+ * the chunking / alignment rules be checked against the reference's chunk plan
+ * (fiber/pool.py:1084-1087) on a machine without a GPU. */
+typedef struct fbr_plan {
+    uint32_t unit_tasks;      /* tasks per claim unit (ring slot) */
+    uint32_t slot_stride;     /* bytes per ring slot (multiple of 16) */
+    uint64_t n_units;         /* claim units of the whole map */
+    uint64_t block_first;     /* worker's block: first task */
+    uint64_t block_count;     /*                 number of tasks */
+} fbr_plan_t;
+int fbr_plan_query(int func_id, uint64_t n_tasks, uint32_t chunksize, uint64_t ring_bytes, int n_workers,
+                   int worker, int sm_count, fbr_plan_t* plan);
+
 /* ---- result collection ----------------------------------------------------------------------
  * fbr_result_wait    <- MapResult.get -> Inventory.get (fiber/pool.py:736-737, 666-679)
  * fbr_result_poll    <- Inventory.iget_ordered / iget_unordered progress (fiber/pool.py:681-728)

@@ -210,3 +210,43 @@ def test_express_and_queue_symbols_need_a_gpu_to_start():
     x = ctypes.c_void_p()
     assert lib.fbr_express_create(0, 0, ctypes.byref(x)) == _abi.FBR_ENODEV
     assert b"no CPU fallback" in lib.fbr_express_last_error()
+
+
+def _plan(body, n, cs=0, ring=0, nw=1, w=0, sms=148):
+    p = _abi.Plan()
+    _abi.check(_abi.load().fbr_plan_query(registry.spec(body).func_id, n, cs, ring, nw, w, sms, ctypes.byref(p)))
+    return p
+
+
+def test_claim_unit_planning_rules():
+    """Host logic of fbr_map_submit without a device: claim units vs the reference's chunk plan."""
+    from oracle.zpool_port import chunk_plan
+    # default chunksize 32 (fiber/pool.py:1169-1170): every reference chunk lies inside one claim unit
+    for body, n in (("pi_inside_det", 10 ** 8), ("square_i64", 10 ** 6), ("payload_map_4k", 10 ** 6), ("payload_checksum_4k", 10 ** 5)):
+        p = _plan(body, n)
+        spec = registry.spec(body)
+        assert p.unit_tasks % 32 == 0 and p.block_first == 0 and p.block_count == n
+        assert p.slot_stride % 16 == 0 and p.slot_stride == p.unit_tasks * spec.result_bytes
+        assert p.n_units == -(-n // p.unit_tasks)
+        for start, count in chunk_plan(min(n, 50000))[::97]:
+            assert start // p.unit_tasks == (start + count - 1) // p.unit_tasks
+    assert _plan("pi_inside_det", 10 ** 8).unit_tasks == 4096 and _plan("payload_map_4k", 10 ** 6).unit_tasks == 32
+    # odd chunk sizes keep slots 16-byte aligned (unit is a multiple of lcm(chunksize, 16/R))
+    for cs in (1, 3, 7, 100, 1000):
+        p = _plan("pi_inside_det", 10 ** 7, cs)
+        assert p.unit_tasks % 16 == 0 and (cs > 4096 or p.unit_tasks % cs == 0)
+        p = _plan("square_i64", 10 ** 6, cs)
+        assert (p.unit_tasks * 8) % 16 == 0
+    # one-task bodies dispatch task by task (tests/test_pool.py:179-234: chunksize 1 must not batch)
+    assert _plan("parzen_f64", 102, 1).unit_tasks == 1 and _plan("sleep_f64", 9, 1).unit_tasks == 1
+    # small maps shrink the unit so the work still spreads over the SMs; tiny rings clamp it
+    assert _plan("pi_inside_det", 20000).unit_tasks < 4096
+    p = _plan("payload_map_4k", 1000, ring=64 << 10)
+    assert p.unit_tasks * 4096 <= 64 << 10
+    # contiguous, complete, unit-aligned blocks per worker (PUSH round-robin with chunk = block)
+    n = 10 ** 6
+    blocks = [_plan("payload_map_4k", n, nw=8, w=w) for w in range(8)]
+    assert blocks[0].block_first == 0 and sum(b.block_count for b in blocks) == n
+    assert all(blocks[i].block_first + blocks[i].block_count == blocks[i + 1].block_first for i in range(7))
+    assert all(b.block_first % 32 == 0 for b in blocks)
+    assert _abi.load().fbr_plan_query(999, 1, 0, 0, 1, 0, 0, ctypes.byref(_abi.Plan())) == _abi.FBR_EINVAL
