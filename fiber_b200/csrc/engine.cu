@@ -708,8 +708,11 @@ static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry
     if (!cx.full_window || cx.host_args) {
         const uint64_t bytes_per_task = std::max<uint64_t>(R, cx.host_args ? d.arg_stride : 0);
         const uint64_t min_wave_tasks = round_up(std::max<uint64_t>(1, (8ull << 20) / bytes_per_task), unit);
-        const uint64_t eighth = round_up((part.count + 7) / 8, unit);
-        cx.wave_tasks_cap = std::min(cx.wave_tasks_cap, std::max(min_wave_tasks, eighth));
+        // 8 waves for ~100 MB maps, up to 64 for multi-GB ones (~64 MiB per wave): the first wave's
+        // H2D and the last wave's D2H are the only copies nothing overlaps with
+        const uint64_t n_waves = std::min<uint64_t>(64, std::max<uint64_t>(8, part.count * bytes_per_task / (64ull << 20)));
+        const uint64_t share = round_up((part.count + n_waves - 1) / n_waves, unit);
+        cx.wave_tasks_cap = std::min(cx.wave_tasks_cap, std::max(min_wave_tasks, share));
     }
 
     // staging
