@@ -233,6 +233,7 @@ struct fbr_pool {
     // pinned host segment cache (size class -> free blocks), and live blocks -> class
     std::unordered_map<uint64_t, std::vector<void*>> pin_free;
     std::unordered_map<void*, uint64_t> pin_live;
+    uint64_t pin_cached_bytes = 0;    // bytes sitting in pin_free (bounded by kPinCacheCap)
     // NUMA-split result segments of multi-worker maps: exact byte size -> free blocks; live -> mapped bytes
     std::unordered_map<uint64_t, std::vector<void*>> numa_free;
     std::unordered_map<void*, std::pair<uint64_t, uint64_t>> numa_live;   // ptr -> (key bytes, mapped bytes)
@@ -250,6 +251,8 @@ static uint64_t pin_class(uint64_t bytes) {
     return c;
 }
 
+constexpr uint64_t kPinCacheCap = 24ull << 30;   // keep at most this much idle pinned memory per pool
+
 static int pinned_acquire(fbr_pool* p, uint64_t bytes, void** out) {
     const uint64_t c = pin_class(bytes ? bytes : 1);
     auto& fl = p->pin_free[c];
@@ -257,6 +260,7 @@ static int pinned_acquire(fbr_pool* p, uint64_t bytes, void** out) {
     if (!fl.empty()) {
         ptr = fl.back();
         fl.pop_back();
+        p->pin_cached_bytes -= c;
     } else {
         CK(cudaHostAlloc(&ptr, c, cudaHostAllocPortable));
     }
@@ -268,8 +272,14 @@ static int pinned_acquire(fbr_pool* p, uint64_t bytes, void** out) {
 static void pinned_release(fbr_pool* p, void* ptr) {
     auto it = p->pin_live.find(ptr);
     if (it == p->pin_live.end()) return;
-    p->pin_free[it->second].push_back(ptr);
+    const uint64_t c = it->second;
     p->pin_live.erase(it);
+    if (p->pin_cached_bytes + c > kPinCacheCap) {
+        cudaFreeHost(ptr);            // cache full: give the pages back
+        return;
+    }
+    p->pin_free[c].push_back(ptr);
+    p->pin_cached_bytes += c;
 }
 
 // ---- NUMA-split pinned segments ------------------------------------------------------------------

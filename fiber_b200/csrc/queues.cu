@@ -398,24 +398,32 @@ int fbr_lane_poll(fbr_lane_t* l, int* ready) {
 
 /* SimpleQueue.put / get on the host's own lazily opened endpoints (LazyZConnection,
  * fiber/queues.py:190-249: the reader connects on first use). */
+static std::mutex g_host_lane_mu;   // serialises the lazy creation of a queue's own host endpoints
+
 int fbr_queue_put(fbr_queue_t* q, const fbr_record_t* rec, int timeout_ms) {
     if (!q || !rec) return qfail(FBR_EINVAL, "NULL argument");
-    if (!q->host_writer) {
-        fbr_lane* l = nullptr;
-        int rc = lane_create(q, true, &l);
-        if (rc) return rc;
-        q->host_writer = l;
+    {
+        std::lock_guard<std::mutex> g(g_host_lane_mu);
+        if (!q->host_writer) {
+            fbr_lane* l = nullptr;
+            int rc = lane_create(q, true, &l);
+            if (rc) return rc;
+            q->host_writer = l;
+        }
     }
     return fbr_lane_send(q->host_writer, rec, timeout_ms);
 }
 
 int fbr_queue_get(fbr_queue_t* q, fbr_record_t* rec, int timeout_ms) {
     if (!q || !rec) return qfail(FBR_EINVAL, "NULL argument");
-    if (!q->host_reader) {
-        fbr_lane* l = nullptr;
-        int rc = lane_create(q, false, &l);
-        if (rc) return rc;
-        q->host_reader = l;
+    {
+        std::lock_guard<std::mutex> g(g_host_lane_mu);
+        if (!q->host_reader) {
+            fbr_lane* l = nullptr;
+            int rc = lane_create(q, false, &l);
+            if (rc) return rc;
+            q->host_reader = l;
+        }
     }
     return fbr_lane_recv(q->host_reader, rec, timeout_ms);
 }
