@@ -1265,6 +1265,12 @@ int fbr_result_poll(fbr_pool_t* p, uint64_t seq, uint64_t* n_done) {
             break;
         }
         uint64_t part_done = 0;
+        if (part.cx.full_window && !part.cx.out_dev && !part.cx.keep_on_device) {
+            // the window reaches the host in one copy at the end: nothing is final before that
+            if (cudaEventQuery(part.done) == cudaSuccess) { done += part.count; continue; }
+            cudaGetLastError();
+            break;
+        }
         for (size_t i = 0; i < part.wave_done.size(); ++i) {
             if (cudaEventQuery(part.wave_done[i]) != cudaSuccess) break;
             part_done = part.wave_cum[i];
