@@ -14,6 +14,8 @@ import itertools
 import threading
 
 from . import _abi
+from .backend import get_backend
+from .core import DeviceCommand, JobSpec, ProcessStatus
 from .queues import Connection, SimpleQueuePush, encode
 
 __all__ = ["Process", "device_process", "active_children"]
@@ -86,7 +88,7 @@ class Process:
         self._handle = None
         self._keep = []            # queues whose lanes the device process uses
         self._exitcode = None
-        self._lib = None
+        self._backend = self._job = None
 
     def __repr__(self):
         status = "initial" if self._handle is None else ("started" if self.is_alive() else "stopped[%s]" % self.exitcode)
@@ -137,22 +139,23 @@ class Process:
             (conn,) = a
             (lane_in, k1), (lane_out, k2) = _reader_lane(conn), _writer_lane(conn)
             self._keep += [k1, k2]
-        self._lib = _abi.load()
-        h = ctypes.c_void_p()
-        _abi.qcheck(self._lib.fbr_process_start(
-            self._device, _BODIES[body], lane_in, lane_out, int(ident),
-            ctypes.byref(msg) if msg is not None else None, lst, len(lst) if lst is not None else 0,
-            int(self._idle_timeout * 1000), ctypes.byref(h)))
-        self._handle = h
+        # Process -> JobSpec -> backend.create_job, the reference's layering
+        # (fiber/process.py:187-215 -> popen_fiber_spawn.py:257-284 -> backend.create_job)
+        cmd = DeviceCommand(body=_BODIES[body], lane_in=lane_in, lane_out=lane_out, ident=int(ident), msg=msg,
+                            records=lst, idle_timeout=self._idle_timeout, keepalive=self._keep)
+        meta = getattr(self._target, "__fiber_meta__", {}) or {}
+        spec = JobSpec(command=cmd, name=self.name, cpu=meta.get("cpu"), mem=meta.get("mem"), gpu=self._device)
+        self._backend = get_backend()
+        self._job = self._backend.create_job(spec)
+        self._handle = self._job.data
         with _children_lock:
             _children.append(self)
 
     def _poll(self):
-        alive, code = ctypes.c_int(1), ctypes.c_int(0)
-        _abi.qcheck(self._lib.fbr_process_poll(self._handle, ctypes.byref(alive), ctypes.byref(code)))
-        if not alive.value:
-            self._exitcode = code.value
-        return bool(alive.value)
+        alive = self._backend.get_job_status(self._job) == ProcessStatus.STARTED
+        if not alive:
+            self._exitcode = self._job.exitcode
+        return alive
 
     def is_alive(self):
         if self._handle is None or self._exitcode is not None:
@@ -169,21 +172,18 @@ class Process:
         assert self._handle is not None, "can only join a started process"
         if self._exitcode is not None:
             return
-        rc = self._lib.fbr_process_join(self._handle, -1 if timeout is None else int(timeout * 1000))
-        if rc != _abi.FBR_ETIMEOUT:
-            _abi.qcheck(rc)
-            self._poll()
+        code = self._backend.wait_for_job(self._job, timeout)
+        if code is not None:
+            self._exitcode = code
 
     def terminate(self):
         if self._handle is not None:
-            _abi.qcheck(self._lib.fbr_process_terminate(self._handle))
+            self._backend.terminate_job(self._job)
 
     def handled(self):
-        n = ctypes.c_uint64(0)
-        _abi.qcheck(self._lib.fbr_process_handled(self._handle, ctypes.byref(n)))
-        return n.value
+        return self._backend.handled(self._job)
 
     def __del__(self):
         h, self._handle = getattr(self, "_handle", None), None
-        if h and self._lib is not None:
-            self._lib.fbr_process_destroy(h)
+        if h and getattr(self, "_backend", None) is not None:
+            self._backend.release_job(self._job)

@@ -1,0 +1,110 @@
+"""CPU: the reference's plug-in interfaces the engine sits behind: the Backend ABC +
+registry (fiber/core.py:79-113, fiber/backend.py:56-76) and the SockContext / Socket / ProcessDevice
+shapes (fiber/socket.py:66-82, 379-425)."""
+import multiprocessing as mp
+
+import pytest
+
+import fiber_b200
+from fiber_b200 import backend, core
+from fiber_b200.core import JobSpec, ProcessStatus
+from fiber_b200.socket import LaneContext, ProcessDevice, SockContext, Socket, get_ctx
+
+from . import workloads as W
+
+
+def test_backend_registry_and_contract():                       # tests/test_backend.py:9-35
+    b = backend.get_backend()
+    assert b is backend.get_backend("gpu") and b.name == "gpu" and isinstance(b, core.Backend)
+    with pytest.raises(mp.ProcessError, match="Invalid backend"):
+        backend.get_backend("no_such_backend")
+    assert b.get_listen_addr() == ("gpu", 0, "nvlink") and b.get_job_logs(None) == ""
+    for method in ("create_job", "get_job_status", "wait_for_job", "terminate_job", "get_listen_addr"):
+        with pytest.raises(NotImplementedError):
+            getattr(core.Backend(), method)(*([None] * {"wait_for_job": 2, "get_listen_addr": 0}.get(method, 1)))
+    assert [s.name for s in ProcessStatus] == ["UNKNOWN", "INITIAL", "STARTED", "STOPPED"]
+    a, c = JobSpec(command=["x"], cpu=2, gpu=1), JobSpec(command=["x"], cpu=2, gpu=1)
+    assert a == c and a != JobSpec(command=["x"], cpu=3, gpu=1) and repr(a).startswith("<JobSpec: {")
+    with pytest.raises(TypeError):
+        b.create_job(JobSpec(command=["python", "-c", "pass"]))   # only device commands run here
+
+
+def test_process_goes_through_the_backend():
+    """Fault injection the reference's way (tests/test_process.py:27-39): swap the registered backend
+    for a subclass whose first create_job calls fail; inspect the JobSpec the Process builds."""
+    real = backend.get_backend()
+    seen = []
+
+    class FlakyBackend(type(real)):
+        def __init__(self, n):
+            super().__init__()
+            self.n, self.count = n, 0
+
+        def create_job(self, job_spec):
+            self.count += 1
+            seen.append(job_spec)
+            if self.count <= self.n:
+                raise TimeoutError("injected create_job failure")
+            raise RuntimeError("stop before touching a device")
+
+    backend._backends["gpu"] = FlakyBackend(1)
+    try:
+        q = fiber_b200.SimpleQueue()
+        p = fiber_b200.Process(target=W.put_queue, args=(q, 10), name="spec-probe", device=3)
+        with pytest.raises(TimeoutError):
+            p.start()
+        with pytest.raises(RuntimeError, match="stop before"):
+            fiber_b200.Process(target=W.put_queue, args=(q, 10), name="spec-probe", device=3).start()
+        spec = seen[-1]
+        assert spec.name == "spec-probe" and spec.gpu == 3 and isinstance(spec.command, core.DeviceCommand)
+        assert spec.command.body == fiber_b200._abi.FBR_PROC_PUT_QUEUE and spec.command.lane_out is not None
+        assert fiber_b200.active_children() == []
+    finally:
+        backend._backends["gpu"] = real
+
+
+def test_socket_modes_over_lanes():                              # fiber/socket.py:328-334, 379-413
+    assert isinstance(get_ctx(), SockContext) and repr(Socket(mode="w")) == "Socket<LaneContext,w>"
+    with pytest.raises(ValueError, match="not supported"):
+        Socket(mode="xyz")
+    push = Socket(mode="w")
+    addr = push.bind()                                           # like ZPool's master socket (pool.py:910-914)
+    pull1, pull2 = Socket(mode="r"), Socket(mode="r")
+    pull1.connect(addr)
+    pull2.connect(addr)
+    for s in (pull1, pull2):                                     # connect == open the lane (lazy in Connection)
+        s._sock.conn.poll(0)
+    for i in range(10):
+        push.send(i)
+    got1 = [pull1.recv(5) for _ in range(5)]
+    got2 = [pull2.recv(5) for _ in range(5)]
+    assert sorted(got1 + got2) == list(range(10)) and got1 == [0, 2, 4, 6, 8]      # PUSH round-robin
+    a, b = Socket(mode="rw"), Socket(mode="rw")                  # PAIR
+    b.connect(a.bind())
+    a.send(b"ping")
+    assert b.recv(5) == b"ping"
+    b.send(b"pong")
+    assert a.recv(5) == b"pong"
+    rep, req = Socket(mode="rep"), Socket(mode="req")            # REQ/REP (pool.py:1452, 1576)
+    req.connect(rep.bind())
+    req.send(b"task?")
+    assert rep.recv(5) == b"task?"
+    rep.send(42)
+    assert req.recv(5) == 42
+    with pytest.raises(ConnectionError):
+        Socket(mode="r").connect("lane://999999")
+    for s in (push, pull1, pull2, a, b, rep, req):
+        s.close()
+
+
+def test_process_device_forwarder():                             # fiber/socket.py:416-425, queues.py:262-281
+    d = ProcessDevice("r", "w", ctx=LaneContext())
+    d.start()
+    writers = [Socket(mode="w") for _ in range(2)]
+    for w in writers:
+        w.connect(d.in_addr)
+    reader = Socket(mode="r")
+    reader.connect(d.out_addr)
+    for k in range(6):
+        writers[k % 2].send(k)
+    assert sorted(reader.recv(5) for _ in range(6)) == list(range(6))
