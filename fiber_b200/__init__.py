@@ -13,7 +13,10 @@ import multiprocessing as _mp
 from .meta import meta  # noqa: F401
 from .pool import ApplyResult, MapResult, Pool, ResultArray  # noqa: F401
 from .process import Process, active_children, device_process  # noqa: F401
-from .queues import Connection, Pipe, SimpleQueue  # noqa: F401
+from . import config  # noqa: F401
+from .config import init, reset  # noqa: F401
+from .queues import Connection, Pipe  # noqa: F401
+from .queues import SimpleQueuePush as _SimpleQueuePush
 from .registry import bind, body_names, device_body  # noqa: F401
 
 __version__ = "0.1.0"
@@ -32,3 +35,10 @@ def cpu_count():
 def current_process():
     """fiber/context.py:24: GPU workers are not OS processes, the caller is always the master."""
     return _mp.current_process()
+
+
+def SimpleQueue():
+    """fiber/context.py:47-54: the push queue, unless ``use_push_queue`` was switched off."""
+    if config.use_push_queue:
+        return _SimpleQueuePush()
+    raise NotImplementedError

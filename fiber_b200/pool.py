@@ -403,6 +403,13 @@ class Pool:
         self.start_workers()
 
     @property
+    def n_jobs(self):
+        """Jobs the reference would start for this pool: ceil(processes / cpu_per_job)
+        (fiber/pool.py:1405-1408)."""
+        from . import config
+        return n_jobs(self._processes, config.cpu_per_job)
+
+    @property
     def n_workers(self):
         self.start_workers()
         return self._engine.n_workers

@@ -108,3 +108,24 @@ def test_process_device_forwarder():                             # fiber/socket.
     for k in range(6):
         writers[k % 2].send(k)
     assert sorted(reader.recv(5) for _ in range(6)) == list(range(6))
+
+
+def test_config_precedence_and_knobs(monkeypatch):              # tests/test_config.py:18-55
+    from fiber_b200 import config
+    try:
+        assert config.cpu_per_job == 1 and config.use_push_queue is True
+        monkeypatch.setenv("FIBER_CPU_PER_JOB", "4")
+        fiber_b200.init()
+        assert config.cpu_per_job == 4                            # env beats the default
+        fiber_b200.init(cpu_per_job=2)
+        assert config.cpu_per_job == 2                            # code beats env
+        assert fiber_b200.Pool(9).n_jobs == 5                     # ceil(9 / 2) jobs (fiber/pool.py:1405-1408)
+        with pytest.raises(ValueError):
+            fiber_b200.init(no_such_key=1)
+        fiber_b200.init(use_push_queue=False)
+        with pytest.raises(NotImplementedError):                  # fiber/context.py:53-54
+            fiber_b200.SimpleQueue()
+    finally:
+        monkeypatch.delenv("FIBER_CPU_PER_JOB", raising=False)
+        fiber_b200.reset()
+    assert config.cpu_per_job == 1 and isinstance(fiber_b200.SimpleQueue(), fiber_b200.queues.SimpleQueuePush)
