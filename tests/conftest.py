@@ -10,6 +10,15 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+    # the suite needs libfiber_b200.so: build it in-tree if this checkout has not been built yet
+    # (nvcc cross-compiles without a GPU; on a box without nvcc the prebuilt .so must have travelled)
+    try:
+        from fiber_b200 import build
+        if build.stale():
+            build.build()
+    except Exception as e:      # noqa: BLE001
+        import warnings
+        warnings.warn("could not (re)build libfiber_b200.so: %s" % e)
 
 
 def _have_gpu():
