@@ -308,10 +308,12 @@ class ExpressResult:
 
     def __init__(self, pool, express, spec, ticket):
         self._pool, self._x, self._spec, self._ticket = pool, express, spec, ticket
-        self._done, self._value = False, None
+        self._done, self._value, self._exc = False, None, None
 
     def get(self, timeout=None):
         if self._done:
+            if self._exc is not None:
+                raise self._exc
             return self._value
         buf = (ctypes.c_uint8 * 48)()
         nbytes, err = ctypes.c_uint32(), ctypes.c_uint32()
@@ -323,7 +325,11 @@ class ExpressResult:
             self._done = True
             res = _abi.Result()
             res.err_code, res.err_task = err.value, 0
-            MapResult._raise_task_error(self, res)
+            try:
+                MapResult._raise_task_error(self, res)
+            except Exception as e:      # noqa: BLE001 -- remembered so that a second get() raises again
+                self._exc = e
+                raise
         _abi.xcheck(rc)
         self._value, self._done = self._spec.unpack_result(bytes(buf[: nbytes.value])), True
         self._pool.recv_tasks += 1
