@@ -99,19 +99,23 @@ struct BodyEntry {
     launch_fn launch;
     const void* kernel;
     int max_ctas_per_sm;   // 0 = as many as fit; streaming read+write bodies run best with few, fat streams
+    const void* kernel_index = nullptr;   // the range()-argument instantiation (arg_stride == 0), if the body has one
 };
 
 static const BodyEntry kBodies[F_COUNT] = {
     {"square_i64", 8, 8, FBR_RES_I64, FBR_BODY_INDEX_ARG | FBR_BODY_SUMMABLE, 4096, launch_thread<SquareI64>,
-     (const void*)dispatch_thread_kernel<SquareI64, false>, 0},
+     (const void*)dispatch_thread_kernel<SquareI64, false>, 0,
+     (const void*)dispatch_thread_kernel<SquareI64, true>},
     {"mul2_i64", 16, 8, FBR_RES_I64, FBR_BODY_SUMMABLE, 4096, launch_thread<Mul2I64>,
      (const void*)dispatch_thread_kernel<Mul2I64, false>, 0},
     {"square_scale_i64", 16, 8, FBR_RES_I64, FBR_BODY_SUMMABLE, 4096, launch_thread<SquareScaleI64>,
      (const void*)dispatch_thread_kernel<SquareScaleI64, false>, 0},
     {"identity_i64", 8, 8, FBR_RES_I64, FBR_BODY_INDEX_ARG | FBR_BODY_SUMMABLE, 4096, launch_thread<IdentityI64>,
-     (const void*)dispatch_thread_kernel<IdentityI64, false>, 0},
+     (const void*)dispatch_thread_kernel<IdentityI64, false>, 0,
+     (const void*)dispatch_thread_kernel<IdentityI64, true>},
     {"pi_inside_det", 8, 1, FBR_RES_BOOL, FBR_BODY_INDEX_ARG | FBR_BODY_SUMMABLE, 4096, launch_thread<PiInsideDet>,
-     (const void*)dispatch_thread_kernel<PiInsideDet, false>, 0},
+     (const void*)dispatch_thread_kernel<PiInsideDet, false>, 0,
+     (const void*)dispatch_thread_kernel<PiInsideDet, true>},
     {"parzen_f32", 8, 16, FBR_RES_F64X2, FBR_BODY_NEEDS_SHARED, 1, launch_parzen<float>,
      (const void*)dispatch_parzen_kernel<float>, 0},
     {"parzen_f64", 8, 16, FBR_RES_F64X2, FBR_BODY_NEEDS_SHARED, 1, launch_parzen<double>,
@@ -122,7 +126,8 @@ static const BodyEntry kBodies[F_COUNT] = {
      (const void*)dispatch_payload_checksum_kernel, 0},
     {"sleep_f64", 8, 1, FBR_RES_NONE, 0, 1, launch_thread<SleepF64>, (const void*)dispatch_thread_kernel<SleepF64, false>, 0},
     {"fault_identity_i64", 8, 8, FBR_RES_I64, FBR_BODY_INDEX_ARG | FBR_BODY_SUMMABLE, 2, launch_thread<FaultIdentityI64>,
-     (const void*)dispatch_thread_kernel<FaultIdentityI64, false>, 0},
+     (const void*)dispatch_thread_kernel<FaultIdentityI64, false>, 0,
+     (const void*)dispatch_thread_kernel<FaultIdentityI64, true>},
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -164,6 +169,7 @@ struct Worker {
     cudaEvent_t ev_out[2];                 // out half's D2H finished
     uint64_t wave_no = 0;
     int occ[F_COUNT];
+    int occ_index[F_COUNT];            // occupancy of the range()-argument instantiations
     int occ_gather = 1, occ_fill = 1, occ_gather_rows = 1;
     std::vector<int> ctrl_free;        // free-list of control-block slots
 };
@@ -384,6 +390,11 @@ static int worker_init(fbr_pool* p, Worker& w, int device) {
         int occ = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kBodies[f].kernel, kThreads, 0));
         w.occ[f] = occ > 0 ? occ : 1;
+        w.occ_index[f] = w.occ[f];
+        if (kBodies[f].kernel_index) {
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kBodies[f].kernel_index, kThreads, 0));
+            w.occ_index[f] = occ > 0 ? occ : 1;
+        }
     }
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w.occ_gather, (const void*)gather_ordered_kernel, kThreads, 0));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w.occ_fill, (const void*)payload_fill_kernel, kThreads, 0));
@@ -434,6 +445,7 @@ static void worker_destroy(Worker& w) {
 static uint32_t pick_unit(const BodyEntry& b, uint32_t chunksize, uint64_t n_tasks, int sm_count, uint64_t ring_bytes) {
     uint32_t pref = b.unit_tasks;
     if (pref == 1) return 1;
+    if (const char* e = getenv("FBR_UNIT_TASKS")) pref = (uint32_t)std::max(16, atoi(e));   // tuning knob (profiles/pi_perf.py)
     // a unit's results (and its argument records) must fit the ring arenas
     const uint64_t per_task = std::max<uint64_t>(std::max(b.result_bytes, b.arg_bytes), 1);
     while (pref > 1 && (uint64_t)pref * per_task > ring_bytes / 2) pref >>= 1;
@@ -522,7 +534,7 @@ static int run_wave(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry& b
     wp.err_word = &w.d_ctrl[slot].err;
     wp.resilient = cx.resilient ? 1u : 0u;
     wp.sum = cx.sum_kind ? &w.d_ctrl[slot].sum : nullptr;
-    int occ_d = w.occ[st.func_id];
+    int occ_d = (d.arg_stride == 0 && body.kernel_index) ? w.occ_index[st.func_id] : w.occ[st.func_id];
     if (body.max_ctas_per_sm) occ_d = std::min(occ_d, body.max_ctas_per_sm);
     if (ov && occ_d > 1) occ_d -= 1;     // leave SM slots for the concurrently running gather CTAs
     if (const char* e = getenv("FBR_DISPATCH_OCC")) occ_d = std::max(1, std::min(occ_d, atoi(e)));
@@ -863,11 +875,10 @@ int fbr_abi_version(void) { return FBR_ABI_VERSION; }
 int fbr_internal_preload(int device) {
     if (cudaSetDevice(device) != cudaSuccess) return FBR_ECUDA;
     cudaFuncAttributes at;
-    for (int f = 0; f < F_COUNT; ++f) cudaFuncGetAttributes(&at, kBodies[f].kernel);
-    cudaFuncGetAttributes(&at, (const void*)dispatch_thread_kernel<SquareI64, true>);
-    cudaFuncGetAttributes(&at, (const void*)dispatch_thread_kernel<IdentityI64, true>);
-    cudaFuncGetAttributes(&at, (const void*)dispatch_thread_kernel<PiInsideDet, true>);
-    cudaFuncGetAttributes(&at, (const void*)dispatch_thread_kernel<FaultIdentityI64, true>);
+    for (int f = 0; f < F_COUNT; ++f) {
+        cudaFuncGetAttributes(&at, kBodies[f].kernel);
+        if (kBodies[f].kernel_index) cudaFuncGetAttributes(&at, kBodies[f].kernel_index);
+    }
     cudaFuncGetAttributes(&at, (const void*)gather_ordered_kernel);
     cudaFuncGetAttributes(&at, (const void*)gather_rows_kernel);
     cudaFuncGetAttributes(&at, (const void*)gather_bulk_kernel);

@@ -89,6 +89,15 @@ struct TicketClaimer {
         __syncthreads();
         return *s_slot;
     }
+    // one-barrier variant: `s_slots[2]` is indexed by iteration parity (see dispatch_thread_kernel)
+    __device__ __forceinline__ uint32_t claim_db(uint32_t* s_slots, uint32_t iter) {
+        if (threadIdx.x == 0) {
+            s_slots[iter & 1] = next;
+            next = atomicAdd(counter, 1u);
+        }
+        __syncthreads();
+        return s_slots[iter & 1];
+    }
 };
 
 // Fold one value per thread into a global accumulator: warp shuffle, then one atomic per warp (no
@@ -112,20 +121,25 @@ __global__ void __launch_bounds__(kThreads) dispatch_thread_kernel(const WavePar
     using Arg = typename B::Arg;
     using Res = typename B::Res;
     constexpr int V = (sizeof(Res) >= 16) ? 1 : (16 / (int)sizeof(Res));
-    __shared__ uint32_t s_ticket;
-    __shared__ int s_fault;
-    const ErrSink es{wp.err_word, &s_fault};
+    // One barrier per unit: the ticket slot (and, for bodies that can lose a unit, the fault flag)
+    // is double-buffered by iteration parity, so the write of iteration i+2 is ordered after the
+    // reads of iteration i by the barrier of iteration i+1.  (Three barriers per 4096-task unit
+    // were 5 % of the pi kernel's stall samples.)
+    __shared__ uint32_t s_ticket[2];
+    __shared__ int s_fault[2];
+    if (threadIdx.x == 0) { s_fault[0] = 0; s_fault[1] = 0; }
 
     TicketClaimer tc{wp.ticket, 0u};
     tc.prime();
     long long acc = 0;            // sum of this thread's results over every unit its CTA completed
-    for (;;) {
-        if (threadIdx.x == 0) s_fault = 0;
-        const uint32_t t = tc.claim(&s_ticket);
+    for (uint32_t iter = 0;; ++iter) {
+        const uint32_t t = tc.claim_db(s_ticket, iter);
         if (t >= wp.n_units) {
             if (wp.sum != nullptr) warp_add(acc, wp.sum);
             return;
         }
+        int* const unit_fault = &s_fault[iter & 1];
+        const ErrSink es{wp.err_word, unit_fault};
         const TaskRecord rec = wp.records[t];
         uint8_t* slot = wp.ring + (size_t)t * wp.slot_stride;
         const uint8_t* uargs = wp.args + rec.arg_off;
@@ -133,60 +147,78 @@ __global__ void __launch_bounds__(kThreads) dispatch_thread_kernel(const WavePar
         uint32_t unit_acc32 = 0;
 
         for (uint32_t base = threadIdx.x * V; base < rec.count; base += kThreads * V) {
-            // results are packed into one 16 B register vector (no local-memory staging)
-            uint32_t pk[4] = {0u, 0u, 0u, 0u};
             // implicit range() argument: one multiply per thread, then strength-reduced adds
-            // (keeps the integer-multiply pipe for the body: Philox needs 20 IMAD.WIDE per task)
+            // (keeps the integer-multiply pipe for the body: Philox needs 18 IMAD.WIDE per task)
             int64_t a_idx = 0;
             if constexpr (kIndex) a_idx = wp.index_start + (int64_t)(rec.first + base) * wp.index_step;
             const uint64_t gidx0 = wp.index_base + rec.first + base;
-#pragma unroll
-            for (int v = 0; v < V; ++v) {
-                const uint32_t i = base + v;
-                Res r = Res{};
-                if (i < rec.count) {
-                    Arg a;
-                    if constexpr (kIndex) a = (Arg)a_idx;
-                    else a = *reinterpret_cast<const Arg*>(uargs + (size_t)i * wp.arg_stride);
-                    r = B::run(a, gidx0 + v, es, rec.attempt);
-                    if constexpr (sizeof(Res) == 8) unit_acc += (long long)r;
-                }
-                if constexpr (kIndex) a_idx += wp.index_step;
-                if constexpr (sizeof(Res) == 1) {
-                    pk[v >> 2] |= (uint32_t)(uint8_t)r << ((v & 3) * 8);
-                } else if constexpr (sizeof(Res) == 8) {
-                    unsigned long long bits;
-                    memcpy(&bits, &r, 8);
-                    pk[2 * v] = (uint32_t)bits;
-                    pk[2 * v + 1] = (uint32_t)(bits >> 32);
-                } else {
-                    static_assert(sizeof(Res) == 1 || sizeof(Res) == 8, "add a packing rule for this result size");
-                }
-            }
-            if constexpr (sizeof(Res) == 1) {     // byte results: fold the packed words with dp4a
-                uint32_t s4 = __dp4a(pk[0], 0x01010101u, 0u);
-                s4 = __dp4a(pk[1], 0x01010101u, s4);
-                s4 = __dp4a(pk[2], 0x01010101u, s4);
-                s4 = __dp4a(pk[3], 0x01010101u, s4);
-                unit_acc32 += s4;
-            }
             uint8_t* dst = slot + (size_t)base * sizeof(Res);
             if (base + V <= rec.count) {
+                // full vector: no per-task bounds checks (a branch per task cost 6 instructions and
+                // serialised the tasks' dependency chains); results are packed into one 16 B
+                // register vector (no local-memory staging)
+                uint32_t pk[4] = {0u, 0u, 0u, 0u};
+                if constexpr (kIndex && B::kVecIndex) {
+                    B::template run_index_vec<V>(a_idx, wp.index_step, pk);
+                } else {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        Arg a;
+                        if constexpr (kIndex) { a = (Arg)a_idx; a_idx += wp.index_step; }
+                        else a = *reinterpret_cast<const Arg*>(uargs + (size_t)(base + v) * wp.arg_stride);
+                        const Res r = B::run(a, gidx0 + v, es, rec.attempt);
+                        if constexpr (sizeof(Res) == 1) {
+                            pk[v >> 2] |= (uint32_t)(uint8_t)r << ((v & 3) * 8);
+                        } else if constexpr (sizeof(Res) == 8) {
+                            unit_acc += (long long)r;
+                            unsigned long long bits;
+                            memcpy(&bits, &r, 8);
+                            pk[2 * v] = (uint32_t)bits;
+                            pk[2 * v + 1] = (uint32_t)(bits >> 32);
+                        } else {
+                            static_assert(sizeof(Res) == 1 || sizeof(Res) == 8, "add a packing rule for this result size");
+                        }
+                    }
+                }
+                if constexpr (sizeof(Res) == 1) {     // byte results: fold the packed words with dp4a
+                    uint32_t s4 = __dp4a(pk[0], 0x01010101u, 0u);
+                    s4 = __dp4a(pk[1], 0x01010101u, s4);
+                    s4 = __dp4a(pk[2], 0x01010101u, s4);
+                    s4 = __dp4a(pk[3], 0x01010101u, s4);
+                    unit_acc32 += s4;
+                }
                 st_vec(dst, make_uint4(pk[0], pk[1], pk[2], pk[3]));
             } else {
-                const uint32_t nb = (rec.count - base) * (uint32_t)sizeof(Res);
-                for (uint32_t b = 0; b < nb; ++b) dst[b] = (uint8_t)(pk[b >> 2] >> ((b & 3) * 8));
+                // the unit's partial tail vector (at most one per unit): one task at a time, kept
+                // rolled so the kernel holds a single copy of the unrolled body
+#pragma unroll 1
+                for (uint32_t i = base; i < rec.count; ++i) {
+                    Arg a;
+                    if constexpr (kIndex) { a = (Arg)a_idx; a_idx += wp.index_step; }
+                    else a = *reinterpret_cast<const Arg*>(uargs + (size_t)i * wp.arg_stride);
+                    const Res r = B::run(a, gidx0 + (i - base), es, rec.attempt);
+                    if constexpr (sizeof(Res) == 1) unit_acc32 += (uint32_t)(uint8_t)r;
+                    else if constexpr (sizeof(Res) == 8) unit_acc += (long long)r;
+                    memcpy(dst + (size_t)(i - base) * sizeof(Res), &r, sizeof(Res));
+                }
             }
         }
-        __syncthreads();  // s_fault final
-        if (!s_fault) acc += unit_acc + (long long)unit_acc32;   // a lost unit is re-dispatched: never folded twice
+        bool lost = false;
+        if constexpr (B::kCanFault) {
+            __syncthreads();      // every thread's fault reports for this unit are in
+            lost = *unit_fault != 0;
+            // re-arm the other flag for the next unit: its last readers ran before this barrier,
+            // its next writers run after the next claim barrier
+            if (threadIdx.x == 0) s_fault[(iter + 1) & 1] = 0;
+        }
+        if (!lost) acc += unit_acc + (long long)unit_acc32;   // a lost unit is re-dispatched: never folded twice
         if (threadIdx.x == 0) {
             // A dead worker loses its whole chunk.  ResilientZPool re-queues it; in the plain ZPool
             // the map would hang forever (fiber/pool.py:801-824 has no try/except) -- here it is
             // reported as a task error instead.
-            if (s_fault && !wp.resilient)
+            if (lost && !wp.resilient)
                 atomicMin(wp.err_word, (unsigned long long)(((wp.index_base + rec.first) << 8) | TASK_FAULT));
-            wp.headers[t] = SlotHeader{rec.seq, rec.count | ((s_fault && wp.resilient) ? kUnitLost : 0u), rec.first};
+            wp.headers[t] = SlotHeader{rec.seq, rec.count | ((lost && wp.resilient) ? kUnitLost : 0u), rec.first};
         }
     }
 }
