@@ -102,14 +102,15 @@ __device__ __forceinline__ void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, ui
 // round 1 multiplies a zero word (free) and round 2's M0 * (hi ^ key) is the same for every task
 // whose index shares the high word -- `hk` is that product, computed once per 16 tasks.  18 wide
 // multiplies per task instead of 20; bit-identical to philox4x32_10 by construction (and by test).
-__device__ __forceinline__ uint8_t pi_inside_det_lo(uint32_t lo, uint2 hk /* (hi, lo) of M0 * (p_hi ^ K) */) {
+__device__ __forceinline__ void philox_block_lo(uint32_t lo, uint2 hk /* (hi, lo) of M0 * (p_hi ^ K) */,
+                                                uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3) {
     constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u, K = 0xF1BE5EEDu;
     // round 1: c = (lo, hi, 0, 0), k = (K, 0)      -> c = (hi ^ K, 0, hi(M0*lo), lo(M0*lo))
     uint32_t p1h, p1l, p2h, p2l;
     mulhilo(M0, lo, p1h, p1l);
     // round 2: k = (K + W0, W1)                    -> c = (hi(M1*c2) ^ k0, lo(M1*c2), hk.hi ^ c3 ^ k1, hk.lo)
     mulhilo(M1, p1h, p2h, p2l);
-    uint32_t c0 = p2h ^ (K + W0), c1 = p2l, c2 = hk.x ^ p1l ^ W1, c3 = hk.y;
+    c0 = p2h ^ (K + W0); c1 = p2l; c2 = hk.x ^ p1l ^ W1; c3 = hk.y;
     uint32_t k0 = K + 2u * W0, k1 = 2u * W1;
 #pragma unroll
     for (int r = 2; r < 10; ++r) {
@@ -120,8 +121,39 @@ __device__ __forceinline__ uint8_t pi_inside_det_lo(uint32_t lo, uint2 hk /* (hi
         c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
         k0 += W0; k1 += W1;
     }
+}
+__device__ __forceinline__ uint8_t pi_inside_det_lo(uint32_t lo, uint2 hk) {
+    uint32_t c0, c1, c2, c3;
+    philox_block_lo(lo, hk, c0, c1, c2, c3);
     return pi_inside_from_block(c0, c1, c2, c3);
 }
+
+// fp32 screen of x*x + y*y < 1 on the top 23 bits of each coordinate (no int->double conversion, no
+// FP64: those instructions hold the SM sub-partition's dispatch port for 8 / 2 cycles each and cost
+// the multiply pipe 26 % of its issue slots -- profiles/microbench/imad_peak.cu).
+//   xf = (c0 >> 9) * 2^-23 exactly ((1 + xf) - 1 with the fraction funnel-shifted under the exponent
+//   of 1.0f), so x is in [xf, xf + 2^-23), likewise y, and with S = x^2 + y^2, Sf = xf^2 + yf^2:
+//       Sf <= S < Sf + 2^-22 (xf + yf) + 2^-45 < Sf + 2^-21 + 2^-45
+//   d = fma(xf, xf, fma(yf, yf, -1)) differs from Sf - 1 by at most two roundings of values <= 1,
+//   i.e. by less than 2^-23, hence |(S - 1) - d| < 2^-20.
+//   The float64 value the reference compares, fl(fl(x*x) + fl(y*y)), is within 2^-51 of S.
+// So whenever |d| >= 2^-19 the sign of d IS the reference's answer (d < 0: inside); the caller
+// re-evaluates the (about 3 in 10^6) closer points in float64.  `dmin` tracks min |d|.
+__device__ __forceinline__ float pi_screen(uint32_t c0, uint32_t c2, float& dmin) {
+    const float xf = __fadd_rn(__uint_as_float(__funnelshift_r(c0, 0x7Fu, 9)), -1.0f);
+    const float yf = __fadd_rn(__uint_as_float(__funnelshift_r(c2, 0x7Fu, 9)), -1.0f);
+    const float d = __fmaf_rn(xf, xf, __fmaf_rn(yf, yf, -1.0f));
+    dmin = fminf(dmin, fabsf(d));
+    return d;
+}
+// four screen values -> four result bytes (0/1): the answer is the sign bit of d, so gather the top
+// bytes with three PRMTs and keep bit 7 of each -- 5 instructions instead of 4 x (FSETP, SEL, LOP3)
+__device__ __forceinline__ uint32_t pi_pack4(float d0, float d1, float d2, float d3) {
+    const uint32_t w01 = __byte_perm(__float_as_uint(d0), __float_as_uint(d1), 0x0073);
+    const uint32_t w23 = __byte_perm(__float_as_uint(d2), __float_as_uint(d3), 0x0073);
+    return (__byte_perm(w01, w23, 0x5410) >> 7) & 0x01010101u;
+}
+constexpr float kPiScreenMargin = 0x1.0p-19f;
 
 // SplitMix64 finaliser; oracle/bodies.py:splitmix64.
 __device__ __host__ __forceinline__ uint64_t splitmix64(uint64_t x) {
@@ -215,9 +247,28 @@ struct PiInsideDet {
             const uint32_t hx = hi ^ 0xF1BE5EEDu;
             const uint2 hk = make_uint2(__umulhi(0xD2511F53u, hx), 0xD2511F53u * hx);
             const uint32_t lo0 = (uint32_t)u0, lstep = (uint32_t)(uint64_t)step;
+            static_assert(V % 4 == 0, "results are packed four to a word");
+            float dmin = 1.0f;
 #pragma unroll
-            for (int v = 0; v < V; ++v)
-                pk[v >> 2] |= (uint32_t)pi_inside_det_lo(lo0 + (uint32_t)v * lstep, hk) << ((v & 3) * 8);
+            for (int g = 0; g < V / 4; ++g) {
+                float d[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    uint32_t c0, c1, c2, c3;
+                    philox_block_lo(lo0 + (uint32_t)(4 * g + k) * lstep, hk, c0, c1, c2, c3);
+                    d[k] = pi_screen(c0, c2, dmin);
+                }
+                pk[g] = pi_pack4(d[0], d[1], d[2], d[3]);
+            }
+            if (dmin < kPiScreenMargin) {
+                // some point of this vector is within 2^-19 of the circle: redo the vector in float64
+                pk[0] = pk[1] = pk[2] = pk[3] = 0u;
+#pragma unroll 1
+                for (int v = 0; v < V; ++v) {
+                    const uint32_t r = pi_inside_det_lo(lo0 + (uint32_t)v * lstep, hk);
+                    pk[v >> 2] |= r << ((v & 3) * 8);
+                }
+            }
         } else {
 #pragma unroll 1
             for (int v = 0; v < V; ++v) {

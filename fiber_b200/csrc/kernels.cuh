@@ -113,96 +113,101 @@ __device__ __forceinline__ void warp_add(long long v, long long* target) {
 // dispatch: ThreadBody -- one thread per task, V = 16/sizeof(Res) consecutive tasks per thread so
 // each thread emits one 16 B store; a warp writes 512 contiguous bytes of the ring slot.
 // ================================================================================================
-// kIndex: the task index itself is the argument (range()); a separate instantiation keeps each
-// kernel to one copy of the unrolled body (the two-path version was 45 KB of SASS, beyond the 32 KB
-// instruction cache level).
+// The slice of one unit that thread `vt` (0..kThreads-1) of the unit's thread grid owns: vectors
+// vt, vt + kThreads, ...  Adds the slice's results to unit_acc / unit_acc32.
 template <class B, bool kIndex>
-__global__ void __launch_bounds__(kThreads) dispatch_thread_kernel(const WaveParams wp) {
+__device__ __forceinline__ void run_unit_slice(const WaveParams& wp, const TaskRecord& rec, uint8_t* slot, uint32_t vt,
+                                               const ErrSink& es, long long& unit_acc, uint32_t& unit_acc32) {
     using Arg = typename B::Arg;
     using Res = typename B::Res;
     constexpr int V = (sizeof(Res) >= 16) ? 1 : (16 / (int)sizeof(Res));
-    // One barrier per unit: the ticket slot (and, for bodies that can lose a unit, the fault flag)
-    // is double-buffered by iteration parity, so the write of iteration i+2 is ordered after the
-    // reads of iteration i by the barrier of iteration i+1.  (Three barriers per 4096-task unit
-    // were 5 % of the pi kernel's stall samples.)
+    const uint8_t* uargs = wp.args + rec.arg_off;
+    for (uint32_t base = vt * V; base < rec.count; base += kThreads * V) {
+        // implicit range() argument: one multiply per thread, then strength-reduced adds
+        // (keeps the integer-multiply pipe for the body: Philox needs 18 IMAD.WIDE per task)
+        int64_t a_idx = 0;
+        if constexpr (kIndex) a_idx = wp.index_start + (int64_t)(rec.first + base) * wp.index_step;
+        const uint64_t gidx0 = wp.index_base + rec.first + base;
+        uint8_t* dst = slot + (size_t)base * sizeof(Res);
+        if (base + V <= rec.count) {
+            // full vector: no per-task bounds checks (a branch per task cost 6 instructions and
+            // serialised the tasks' dependency chains); results are packed into one 16 B
+            // register vector (no local-memory staging)
+            uint32_t pk[4] = {0u, 0u, 0u, 0u};
+            if constexpr (kIndex && B::kVecIndex) {
+                B::template run_index_vec<V>(a_idx, wp.index_step, pk);
+            } else {
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    Arg a;
+                    if constexpr (kIndex) { a = (Arg)a_idx; a_idx += wp.index_step; }
+                    else a = *reinterpret_cast<const Arg*>(uargs + (size_t)(base + v) * wp.arg_stride);
+                    const Res r = B::run(a, gidx0 + v, es, rec.attempt);
+                    if constexpr (sizeof(Res) == 1) {
+                        pk[v >> 2] |= (uint32_t)(uint8_t)r << ((v & 3) * 8);
+                    } else if constexpr (sizeof(Res) == 8) {
+                        unit_acc += (long long)r;
+                        unsigned long long bits;
+                        memcpy(&bits, &r, 8);
+                        pk[2 * v] = (uint32_t)bits;
+                        pk[2 * v + 1] = (uint32_t)(bits >> 32);
+                    } else {
+                        static_assert(sizeof(Res) == 1 || sizeof(Res) == 8, "add a packing rule for this result size");
+                    }
+                }
+            }
+            if constexpr (sizeof(Res) == 1) {     // byte results: fold the packed words with dp4a
+                uint32_t s4 = __dp4a(pk[0], 0x01010101u, 0u);
+                s4 = __dp4a(pk[1], 0x01010101u, s4);
+                s4 = __dp4a(pk[2], 0x01010101u, s4);
+                s4 = __dp4a(pk[3], 0x01010101u, s4);
+                unit_acc32 += s4;
+            }
+            st_vec(dst, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+        } else {
+            // the unit's partial tail vector (at most one per unit): one task at a time, kept
+            // rolled so the kernel holds a single copy of the unrolled body
+#pragma unroll 1
+            for (uint32_t i = base; i < rec.count; ++i) {
+                Arg a;
+                if constexpr (kIndex) { a = (Arg)a_idx; a_idx += wp.index_step; }
+                else a = *reinterpret_cast<const Arg*>(uargs + (size_t)i * wp.arg_stride);
+                const Res r = B::run(a, gidx0 + (i - base), es, rec.attempt);
+                if constexpr (sizeof(Res) == 1) unit_acc32 += (uint32_t)(uint8_t)r;
+                else if constexpr (sizeof(Res) == 8) unit_acc += (long long)r;
+                memcpy(dst + (size_t)(i - base) * sizeof(Res), &r, sizeof(Res));
+            }
+        }
+    }
+}
+
+// kIndex: the task index itself is the argument (range()); a separate instantiation keeps each
+// kernel to one copy of the unrolled body (the two-path version was 45 KB of SASS, beyond the 32 KB
+// instruction cache level).
+//
+// One barrier per unit: the ticket slot (and, for bodies that can lose a unit, the fault flag) is
+// double-buffered by iteration parity, so the write of iteration i+2 is ordered after the reads of
+// iteration i by the barrier of iteration i+1.  (Three barriers per 4096-task unit were 5 % of the
+// pi kernel's stall samples.  Tried and dropped: warp-granular claims with no barrier at all --
+// 0.2689 ms against 0.2654 ms on the 1e8-task pi wave; the skew between a CTA's warps is not what
+// limits this kernel.)
+template <class B, bool kIndex>
+__global__ void __launch_bounds__(kThreads) dispatch_thread_kernel(const WaveParams wp) {
     __shared__ uint32_t s_ticket[2];
     __shared__ int s_fault[2];
     if (threadIdx.x == 0) { s_fault[0] = 0; s_fault[1] = 0; }
-
     TicketClaimer tc{wp.ticket, 0u};
     tc.prime();
     long long acc = 0;            // sum of this thread's results over every unit its CTA completed
     for (uint32_t iter = 0;; ++iter) {
         const uint32_t t = tc.claim_db(s_ticket, iter);
-        if (t >= wp.n_units) {
-            if (wp.sum != nullptr) warp_add(acc, wp.sum);
-            return;
-        }
+        if (t >= wp.n_units) break;
         int* const unit_fault = &s_fault[iter & 1];
         const ErrSink es{wp.err_word, unit_fault};
         const TaskRecord rec = wp.records[t];
-        uint8_t* slot = wp.ring + (size_t)t * wp.slot_stride;
-        const uint8_t* uargs = wp.args + rec.arg_off;
         long long unit_acc = 0;
         uint32_t unit_acc32 = 0;
-
-        for (uint32_t base = threadIdx.x * V; base < rec.count; base += kThreads * V) {
-            // implicit range() argument: one multiply per thread, then strength-reduced adds
-            // (keeps the integer-multiply pipe for the body: Philox needs 18 IMAD.WIDE per task)
-            int64_t a_idx = 0;
-            if constexpr (kIndex) a_idx = wp.index_start + (int64_t)(rec.first + base) * wp.index_step;
-            const uint64_t gidx0 = wp.index_base + rec.first + base;
-            uint8_t* dst = slot + (size_t)base * sizeof(Res);
-            if (base + V <= rec.count) {
-                // full vector: no per-task bounds checks (a branch per task cost 6 instructions and
-                // serialised the tasks' dependency chains); results are packed into one 16 B
-                // register vector (no local-memory staging)
-                uint32_t pk[4] = {0u, 0u, 0u, 0u};
-                if constexpr (kIndex && B::kVecIndex) {
-                    B::template run_index_vec<V>(a_idx, wp.index_step, pk);
-                } else {
-#pragma unroll
-                    for (int v = 0; v < V; ++v) {
-                        Arg a;
-                        if constexpr (kIndex) { a = (Arg)a_idx; a_idx += wp.index_step; }
-                        else a = *reinterpret_cast<const Arg*>(uargs + (size_t)(base + v) * wp.arg_stride);
-                        const Res r = B::run(a, gidx0 + v, es, rec.attempt);
-                        if constexpr (sizeof(Res) == 1) {
-                            pk[v >> 2] |= (uint32_t)(uint8_t)r << ((v & 3) * 8);
-                        } else if constexpr (sizeof(Res) == 8) {
-                            unit_acc += (long long)r;
-                            unsigned long long bits;
-                            memcpy(&bits, &r, 8);
-                            pk[2 * v] = (uint32_t)bits;
-                            pk[2 * v + 1] = (uint32_t)(bits >> 32);
-                        } else {
-                            static_assert(sizeof(Res) == 1 || sizeof(Res) == 8, "add a packing rule for this result size");
-                        }
-                    }
-                }
-                if constexpr (sizeof(Res) == 1) {     // byte results: fold the packed words with dp4a
-                    uint32_t s4 = __dp4a(pk[0], 0x01010101u, 0u);
-                    s4 = __dp4a(pk[1], 0x01010101u, s4);
-                    s4 = __dp4a(pk[2], 0x01010101u, s4);
-                    s4 = __dp4a(pk[3], 0x01010101u, s4);
-                    unit_acc32 += s4;
-                }
-                st_vec(dst, make_uint4(pk[0], pk[1], pk[2], pk[3]));
-            } else {
-                // the unit's partial tail vector (at most one per unit): one task at a time, kept
-                // rolled so the kernel holds a single copy of the unrolled body
-#pragma unroll 1
-                for (uint32_t i = base; i < rec.count; ++i) {
-                    Arg a;
-                    if constexpr (kIndex) { a = (Arg)a_idx; a_idx += wp.index_step; }
-                    else a = *reinterpret_cast<const Arg*>(uargs + (size_t)i * wp.arg_stride);
-                    const Res r = B::run(a, gidx0 + (i - base), es, rec.attempt);
-                    if constexpr (sizeof(Res) == 1) unit_acc32 += (uint32_t)(uint8_t)r;
-                    else if constexpr (sizeof(Res) == 8) unit_acc += (long long)r;
-                    memcpy(dst + (size_t)(i - base) * sizeof(Res), &r, sizeof(Res));
-                }
-            }
-        }
+        run_unit_slice<B, kIndex>(wp, rec, wp.ring + (size_t)t * wp.slot_stride, threadIdx.x, es, unit_acc, unit_acc32);
         bool lost = false;
         if constexpr (B::kCanFault) {
             __syncthreads();      // every thread's fault reports for this unit are in
@@ -221,6 +226,7 @@ __global__ void __launch_bounds__(kThreads) dispatch_thread_kernel(const WavePar
             wp.headers[t] = SlotHeader{rec.seq, rec.count | ((lost && wp.resilient) ? kUnitLost : 0u), rec.first};
         }
     }
+    if (wp.sum != nullptr) warp_add(acc, wp.sum);
 }
 
 // ================================================================================================

@@ -1,0 +1,133 @@
+// imad_peak.cu -- what the SM's integer-multiply pipe can do, measured (no roofline number for it exists
+// in MEASURED_PEAKS.json).  The pi dispatch kernel is bound by IMAD.WIDE.U32 (Philox4x32-10: two
+// 32x32->64 products per round); this prints the rate of that instruction alone, of the Philox
+// rounds alone (IMAD.WIDE + LOP3 chains, no FP64 tail), and of the full body.
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o profiles/microbench/imad_peak profiles/microbench/imad_peak.cu
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../fiber_b200/csrc/bodies.cuh"
+
+using namespace fbr;
+
+template <int ILP>
+__global__ void __launch_bounds__(256) k_wide(uint32_t* out, int iters, uint32_t seed) {
+    uint32_t x[ILP], acc = 0;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) x[i] = seed + threadIdx.x * 977u + i * 131u + blockIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) {
+            uint32_t hi, lo;
+            mulhilo(0xD2511F53u, x[i], hi, lo);
+            x[i] = hi ^ lo;               // one LOP3 per multiply keeps both halves live
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) acc ^= x[i];
+    if (acc == 0x12345u) out[0] = acc;
+}
+
+// Philox rounds only: 16 tasks per thread like the dispatch kernel, results xor-folded
+__global__ void __launch_bounds__(256) k_philox(uint32_t* out, int iters, uint32_t seed) {
+    uint32_t acc = 0;
+    uint32_t base = seed + (blockIdx.x * 256u + threadIdx.x) * 16u;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int v = 0; v < 16; ++v) {
+            uint32_t c0 = base + v, c1 = 0, c2 = 0, c3 = 0;
+            philox4x32_10(c0, c1, c2, c3, 0xF1BE5EEDu, 0u);
+            acc ^= c0 ^ c1 ^ c2 ^ c3;
+        }
+        base += gridDim.x * 4096u;
+    }
+    if (acc == 0x12345u) out[0] = acc;
+}
+
+// the full pi body (18 wide multiplies + FP64 tail), same shape
+__global__ void __launch_bounds__(256) k_pi(uint32_t* out, int iters, uint32_t seed) {
+    uint32_t acc = 0;
+    uint32_t base = seed + (blockIdx.x * 256u + threadIdx.x) * 16u;
+    const uint32_t hx = 0u ^ 0xF1BE5EEDu;
+    const uint2 hk = make_uint2(__umulhi(0xD2511F53u, hx), 0xD2511F53u * hx);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int v = 0; v < 16; ++v) acc += pi_inside_det_lo(base + v, hk);
+        base += gridDim.x * 4096u;
+    }
+    if (acc == 0x12345u) out[0] = acc;
+}
+
+// the screened body the dispatch kernel runs: Philox + fp32 screen (float64 only for points within
+// 2^-19 of the circle; the re-evaluation is left out here, it runs for ~3 vectors in 10^5)
+__global__ void __launch_bounds__(256) k_pi_screen(uint32_t* out, int iters, uint32_t seed) {
+    uint32_t acc = 0;
+    uint32_t base = seed + (blockIdx.x * 256u + threadIdx.x) * 16u;
+    const uint32_t hx = 0u ^ 0xF1BE5EEDu;
+    const uint2 hk = make_uint2(__umulhi(0xD2511F53u, hx), 0xD2511F53u * hx);
+    float dmin = 1.0f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int v = 0; v < 16; ++v) {
+            uint32_t c0, c1, c2, c3;
+            philox_block_lo(base + v, hk, c0, c1, c2, c3);
+            acc += pi_screen(c0, c2, dmin) < 0.0f ? 1u : 0u;
+        }
+        base += gridDim.x * 4096u;
+    }
+    if (acc == 0x12345u || dmin == 0.123f) out[0] = acc;
+}
+
+template <class F>
+static float time_ms(F launch) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    launch(); launch();
+    cudaDeviceSynchronize();
+    float best = 1e30f;
+    for (int r = 0; r < 5; ++r) {
+        cudaEventRecord(a);
+        launch();
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        float ms; cudaEventElapsedTime(&ms, a, b);
+        if (ms < best) best = ms;
+    }
+    return best;
+}
+
+int main() {
+    cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
+    int clk_khz = 0; cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0);
+    const int sms = p.multiProcessorCount;
+    uint32_t* out; cudaMalloc(&out, 4);
+    printf("{\"device\": \"%s\", \"sms\": %d, \"clock_mhz\": %d", p.name, sms, clk_khz / 1000);
+    const int iters = 2000;
+    for (int occ = 4; occ <= 8; occ += 2) {
+        const int grid = sms * occ;
+        {
+            float ms = time_ms([&] { k_wide<8><<<grid, 256>>>(out, iters, 1u); });
+            double ops = (double)grid * 256 * iters * 8;
+            printf(",\n \"imad_wide_u32_ilp8_occ%d\": {\"ms\": %.4f, \"per_clk_per_sm\": %.2f, \"Gops\": %.1f}", occ, ms,
+                   ops / (ms * 1e-3) / sms / (clk_khz * 1e3), ops / ms * 1e-6);
+        }
+    }
+    for (int occ = 4; occ <= 6; ++occ) {
+        const int grid = sms * occ;
+        const int it2 = 40;
+        float ms = time_ms([&] { k_philox<<<grid, 256>>>(out, it2, 1u); });
+        double tasks = (double)grid * 256 * it2 * 16;
+        printf(",\n \"philox_rounds_only_occ%d\": {\"ms\": %.4f, \"tasks_per_s\": %.4e, \"wide_mul_per_clk_per_sm\": %.2f}", occ, ms,
+               tasks / (ms * 1e-3), tasks * 17 / (ms * 1e-3) / sms / (clk_khz * 1e3));
+        ms = time_ms([&] { k_pi<<<grid, 256>>>(out, it2, 1u); });
+        printf(",\n \"pi_body_f64_occ%d\": {\"ms\": %.4f, \"tasks_per_s\": %.4e, \"wide_mul_per_clk_per_sm\": %.2f}", occ, ms,
+               tasks / (ms * 1e-3), tasks * 18 / (ms * 1e-3) / sms / (clk_khz * 1e3));
+        ms = time_ms([&] { k_pi_screen<<<grid, 256>>>(out, it2, 1u); });
+        printf(",\n \"pi_body_screened_occ%d\": {\"ms\": %.4f, \"tasks_per_s\": %.4e, \"wide_mul_per_clk_per_sm\": %.2f}", occ, ms,
+               tasks / (ms * 1e-3), tasks * 18 / (ms * 1e-3) / sms / (clk_khz * 1e3));
+    }
+    printf("\n}\n");
+    return 0;
+}
