@@ -603,7 +603,10 @@ static int run_wave(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry& b
         const uint32_t group_slots = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((128u << 10) / cx.slot_stride, n_units / (4 * max_ctas)));
         const uint32_t n_groups = (n_units + group_slots - 1) / group_slots;
         const int grid_r = (int)std::min<uint64_t>(n_groups, max_ctas);
-        gather_rows_kernel<<<grid_r, kThreads, 0, s_g>>>(gp, gticket, group_slots);
+        // waves that fit the L2 are gathered newest-slot-first (see the kernel); FBR_GATHER_REVERSE=0/1 overrides
+        bool reverse = (uint64_t)n_units * cx.slot_stride <= (128ull << 20);
+        if (const char* e = getenv("FBR_GATHER_REVERSE")) reverse = atoi(e) != 0;
+        gather_rows_kernel<<<grid_r, kThreads, 0, s_g>>>(gp, gticket, group_slots, reverse);
         CK(cudaMemsetAsync(gticket, 0, sizeof(uint32_t), s_g));
     } else {
         gather_ordered_kernel<<<grid_g, kThreads, 0, s_g>>>(gp);

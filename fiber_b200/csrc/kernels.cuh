@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(kThreads) gather_ordered_kernel(const GatherPa
 // ---- rows: a CTA claims ~128 KB of ring by ticket and streams it as 4 KB rows ---------------------
 // Thread j owns the j-th 16 B column of every row, 4 rows in flight.  Measured on the 8.2 GB payload
 // wave: 99.8 % of the HBM copy peak (the flat kernel: 92 %).
-__global__ void __launch_bounds__(kThreads) gather_rows_kernel(const GatherParams gp, uint32_t* ticket, uint32_t group_slots) {
+__global__ void __launch_bounds__(kThreads) gather_rows_kernel(const GatherParams gp, uint32_t* ticket, uint32_t group_slots, bool reverse) {
     __shared__ uint32_t s_ticket;
     TicketClaimer tc{ticket, 0u};
     tc.prime();
@@ -494,8 +494,11 @@ __global__ void __launch_bounds__(kThreads) gather_rows_kernel(const GatherParam
     };
 
     for (;;) {
-        const uint32_t g = tc.claim(&s_ticket);
-        if (g >= n_groups) break;
+        const uint32_t gt = tc.claim(&s_ticket);
+        if (gt >= n_groups) break;
+        // newest slots first: the dispatch kernel filled the ring in ticket order just before this
+        // launch, so its tail is still in the 126 MB L2 while its head has been written back
+        const uint32_t g = reverse ? n_groups - 1 - gt : gt;
         const uint32_t slot0 = g * group_slots;
         const uint32_t nslots = min(group_slots, gp.n_units - slot0);
         const uint32_t nrows = nslots * rps;
