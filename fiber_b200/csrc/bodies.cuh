@@ -25,7 +25,8 @@ enum FuncId : int32_t {
     F_PAYLOAD_CHECKSUM_4K = 8,  // 4 KB record -> u32
     F_SLEEP_F64 = 9,         // tests/test_pool.py:56-57   sleep_worker(duration) -> None
     F_FAULT_IDENTITY_I64 = 10,  // identity with injected faults (resilient pool tests)
-    F_COUNT = 11
+    F_PI_INSIDE_BITS8 = 11,  // pi_inside_det over 8 consecutive range() indices -> one byte, bit k = index 8g+k
+    F_COUNT = 12
 };
 
 enum TaskError : uint32_t { TASK_OK = 0, TASK_OVERFLOW = 1, TASK_BADARG = 2, TASK_FAULT = 3 };
@@ -276,6 +277,42 @@ struct PiInsideDet {
                 pk[v >> 2] |= r << ((v & 3) * 8);   // v is a run-time index here: rare path (2^32 crossing)
             }
         }
+    }
+    // The same 16 consecutive arguments, one BIT per result: bit v of the return value is
+    // is_inside(a0 + v*step).  (Body pi_inside_bits8: a bool needs one bit, not one byte, on its way
+    // through the ring, the gather and PCIe.)
+    __device__ static __forceinline__ uint32_t run_index_bits16(int64_t a0, int64_t step) {
+        const uint64_t u0 = (uint64_t)a0, u_last = u0 + 15ull * (uint64_t)step;
+        const uint32_t hi = (uint32_t)(u0 >> 32);
+        uint32_t bits = 0;
+        if (hi == (uint32_t)(u_last >> 32)) {
+            const uint32_t hx = hi ^ 0xF1BE5EEDu;
+            const uint2 hk = make_uint2(__umulhi(0xD2511F53u, hx), 0xD2511F53u * hx);
+            const uint32_t lo0 = (uint32_t)u0, lstep = (uint32_t)(uint64_t)step;
+            float dmin = 1.0f;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                float d[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    uint32_t c0, c1, c2, c3;
+                    philox_block_lo(lo0 + (uint32_t)(4 * g + k) * lstep, hk, c0, c1, c2, c3);
+                    d[k] = pi_screen(c0, c2, dmin);
+                }
+                // bytes (b0, b1, b2, b3) of 0/1 -> nibble b0 | b1<<1 | b2<<2 | b3<<3: one multiply moves
+                // byte i's bit to position 28+i (the partial products land on distinct bits: no carries)
+                bits |= ((pi_pack4(d[0], d[1], d[2], d[3]) * 0x10204080u) >> 28) << (4 * g);
+            }
+            if (dmin < kPiScreenMargin) {
+                bits = 0;
+#pragma unroll 1
+                for (int v = 0; v < 16; ++v) bits |= (uint32_t)pi_inside_det_lo(lo0 + (uint32_t)v * lstep, hk) << v;
+            }
+        } else {
+#pragma unroll 1
+            for (int v = 0; v < 16; ++v) bits |= (uint32_t)pi_inside_det((int64_t)(u0 + (uint64_t)v * (uint64_t)step)) << v;
+        }
+        return bits;
     }
 };
 // sleep_worker(duration): busy-wait on the global nanosecond timer; returns None (one pad byte).

@@ -88,6 +88,9 @@ static void launch_payload_map(const WaveParams& wp, int grid, cudaStream_t s) {
 static void launch_payload_checksum(const WaveParams& wp, int grid, cudaStream_t s) {
     dispatch_payload_checksum_kernel<<<grid, kThreads, 0, s>>>(wp);
 }
+static void launch_pi_bits(const WaveParams& wp, int grid, cudaStream_t s) {
+    dispatch_pi_bits_kernel<<<grid, kThreads, 0, s>>>(wp);
+}
 template <typename T>
 static void launch_parzen(const WaveParams& wp, int grid, cudaStream_t s) {
     dispatch_parzen_kernel<T><<<grid, kThreads, 0, s>>>(wp);
@@ -128,6 +131,8 @@ static const BodyEntry kBodies[F_COUNT] = {
     {"fault_identity_i64", 8, 8, FBR_RES_I64, FBR_BODY_INDEX_ARG | FBR_BODY_SUMMABLE, 2, launch_thread<FaultIdentityI64>,
      (const void*)dispatch_thread_kernel<FaultIdentityI64, false>, 0,
      (const void*)dispatch_thread_kernel<FaultIdentityI64, true>},
+    {"pi_inside_bits8", 8, 1, FBR_RES_BITS8, FBR_BODY_INDEX_ARG | FBR_BODY_INDEX_ONLY | FBR_BODY_SUMMABLE, 512, launch_pi_bits,
+     (const void*)dispatch_pi_bits_kernel, 0},
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -1105,6 +1110,8 @@ int fbr_map_submit(fbr_pool_t* p, const fbr_map_desc_t* d, uint64_t* seq_out) {
     if (d->arg_stride == 0) {
         if (!(body.flags & FBR_BODY_INDEX_ARG))
             return fail(FBR_EINVAL, "body %s needs explicit argument records (arg_stride=0)", body.name);
+    } else if (body.flags & FBR_BODY_INDEX_ONLY) {
+        return fail(FBR_EINVAL, "body %s takes range() arguments only (arg_stride must be 0)", body.name);
     } else {
         if (d->arg_stride < body.arg_bytes || (d->arg_stride % 8) != 0)
             return fail(FBR_EINVAL, "arg_stride %u invalid for body %s (arg_bytes %u)", d->arg_stride, body.name, body.arg_bytes);

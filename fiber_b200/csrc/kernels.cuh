@@ -230,6 +230,38 @@ __global__ void __launch_bounds__(kThreads) dispatch_thread_kernel(const WavePar
 }
 
 // ================================================================================================
+// dispatch: pi_inside_bits8 -- task g is the 8 range() indices 8g..8g+7, its result one byte (bit k =
+// is_inside(index 8g+k)).  A thread owns two consecutive bytes of the unit (16 indices, the same
+// Philox vector as the byte-result kernel) and stores them as one uint16; a warp writes 64
+// contiguous bytes.  Algorithmic bytes per index: 0 read + 1/8 written.
+// ================================================================================================
+__global__ void __launch_bounds__(kThreads) dispatch_pi_bits_kernel(const WaveParams wp) {
+    __shared__ uint32_t s_ticket[2];
+    TicketClaimer tc{wp.ticket, 0u};
+    tc.prime();
+    long long acc = 0;
+    for (uint32_t iter = 0;; ++iter) {
+        const uint32_t t = tc.claim_db(s_ticket, iter);
+        if (t >= wp.n_units) break;
+        const TaskRecord rec = wp.records[t];
+        uint8_t* slot = wp.ring + (size_t)t * wp.slot_stride;
+        for (uint32_t b = threadIdx.x * 2; b < rec.count; b += kThreads * 2) {
+            const int64_t a0 = wp.index_start + (int64_t)((rec.first + b) * 8ull) * wp.index_step;
+            const uint32_t bits = PiInsideDet::run_index_bits16(a0, wp.index_step);
+            if (b + 2 <= rec.count) {
+                *reinterpret_cast<uint16_t*>(slot + b) = (uint16_t)bits;
+                acc += __popc(bits);
+            } else {                                  // odd byte count: the unit's last byte
+                slot[b] = (uint8_t)bits;
+                acc += __popc(bits & 0xffu);
+            }
+        }
+        if (threadIdx.x == 0) wp.headers[t] = SlotHeader{rec.seq, rec.count, rec.first};
+    }
+    if (wp.sum != nullptr) warp_add(acc, wp.sum);
+}
+
+// ================================================================================================
 // dispatch: payload_map_4k -- a CTA streams its unit's 4 KB records: thread j owns the j-th 16 B
 // column of every record, 4 records in flight per thread (16 KB per CTA in flight).
 //   out[w] = in[w] * 2654435761 + t   (u32 wrap), t = global task index.

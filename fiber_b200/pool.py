@@ -96,18 +96,28 @@ class ResultArray(collections.abc.Sequence):
     nothing, indexing fetches just the requested range, and the full array crosses PCIe only when
     something needs all of it (``array``, ``tolist()``, iteration, ``==``)."""
 
-    def __init__(self, spec, array, device_sum=None, n=None, fetch=None):
+    def __init__(self, spec, array, device_sum=None, n=None, fetch=None, bits=None):
         self._spec = spec
         self._arr = array
         self._sum = device_sum
         self._n = len(array) if array is not None else n
         self._fetch = fetch            # (lo, hi) -> ndarray, for device-resident results
+        self._bits = bits              # Pool(results="bits"): uint8[ceil(n/8)], bit k of byte j = result 8j+k
 
     @property
     def _a(self):
         if self._arr is None:
-            self._arr = self._fetch(0, self._n)
+            if self._bits is not None:
+                self._arr = np.unpackbits(self._bits, count=self._n, bitorder="little").view(np.bool_)
+            else:
+                self._arr = self._fetch(0, self._n)
         return self._arr
+
+    @property
+    def packed(self):
+        """The bit-packed results (``Pool(results="bits")``): zero-copy uint8 view of the pinned
+        segment, result i at bit ``i & 7`` of byte ``i >> 3``; ``None`` for byte-per-result maps."""
+        return self._bits
 
     @property
     def on_device(self):
@@ -117,7 +127,20 @@ class ResultArray(collections.abc.Sequence):
         return self._n
 
     def __getitem__(self, i):
-        if self._arr is None:
+        if self._arr is None and self._bits is not None:
+            # bit-backed: single results and contiguous ranges are read straight from the packed bytes
+            if isinstance(i, slice):
+                lo, hi, step = i.indices(self._n)
+                if step == 1:
+                    hi = max(lo, hi)
+                    part = np.unpackbits(self._bits[lo >> 3:(hi + 7) >> 3], bitorder="little")
+                    return part[lo & 7:(lo & 7) + hi - lo].view(np.bool_).tolist()
+            else:
+                j = i + self._n if i < 0 else i
+                if not 0 <= j < self._n:
+                    raise IndexError("ResultArray index out of range")
+                return bool((int(self._bits[j >> 3]) >> (j & 7)) & 1)
+        elif self._arr is None:
             if isinstance(i, slice):
                 lo, hi, step = i.indices(self._n)
                 if step == 1:
@@ -134,10 +157,12 @@ class ResultArray(collections.abc.Sequence):
     def __iter__(self):
         step = 1 << 16
         for s in range(0, self._n, step):
-            yield from self._spec.rows_to_list(self._a[s:s + step])
+            yield from self[s:s + step]
 
     def __eq__(self, other):
         if isinstance(other, ResultArray):
+            if self._bits is not None and other._bits is not None:
+                return self._n == other._n and np.array_equal(self._bits, other._bits)
             return np.array_equal(self._a, other._a)
         if isinstance(other, (list, tuple)):
             return len(other) == len(self) and self.tolist() == list(other)
@@ -147,6 +172,7 @@ class ResultArray(collections.abc.Sequence):
         n = len(self)
         head = self[:6]
         return "ResultArray(%s%s, len=%d, body=%s%s)" % (head, "..." if n > 6 else "", n, self._spec.name,
+                                                         ", bit-packed" if self._bits is not None else
                                                          ", on device" if self._arr is None else "")
 
     def __array__(self, dtype=None, copy=None):
@@ -164,6 +190,8 @@ class ResultArray(collections.abc.Sequence):
     def sum(self):
         if self._sum is not None:
             return self._sum
+        if self._bits is not None:
+            return int(np.unpackbits(self._bits).sum())   # the bits past n are zero
         return int(self._a.sum())
 
     def sort(self):
@@ -179,13 +207,16 @@ class MapResult:
         self._result = None
         self._segment = None
         self._yielded = False
+        self._n_items = None          # bit-packed maps: number of range() indices (n = ceil(n_items / 8) byte tasks)
+        self._user_spec = spec
 
     # -- internal ----------------------------------------------------------------------------
     def _wait(self, timeout=None):
         if self._result is not None:
             return self._result
         if self._n == 0:
-            self._result = ResultArray(self._spec, np.empty((0,) + self._spec.result_dtype()[1], self._spec.result_dtype()[0]), 0)
+            us = self._user_spec
+            self._result = ResultArray(us, np.empty((0,) + us.result_dtype()[1], us.result_dtype()[0]), 0)
             return self._result
         res = _abi.Result()
         eng = self._engine
@@ -198,7 +229,7 @@ class MapResult:
             self._raise_task_error(res)
         _abi.check(rc)
         self._keepalive = None
-        self._pool.recv_tasks += self._n
+        self._pool.recv_tasks += self._n if self._n_items is None else self._n_items
         dtype, sub = self._spec.result_dtype()
         dsum = int(res.sum) if (self._flags & _abi.FBR_WANT_SUM) else None
         self.n_waves = res.n_waves
@@ -217,6 +248,19 @@ class MapResult:
         seg = _Segment(eng, self._seq, res.data, res.n_tasks * res.result_bytes)
         arr = np.asarray(seg).view(dtype).reshape((res.n_tasks,) + sub)
         self._segment = seg
+        if self._n_items is not None:
+            # bit-packed map (pi_inside_bits8): `arr` holds ceil(n/8) bytes.  The body evaluated all 8
+            # indices of the last byte; the ones past the end of the range are dropped here, from the
+            # byte and from the folded count.
+            n, extra = self._n_items, (-self._n_items) % 8
+            if extra:
+                last = int(arr[-1])
+                keep = last & (0xFF >> extra)
+                if dsum is not None:
+                    dsum -= bin(last ^ keep).count("1")
+                arr[-1] = keep
+            self._result = ResultArray(self._user_spec, None, dsum, n=n, bits=arr)
+            return self._result
         self._result = ResultArray(self._spec, arr, dsum)
         return self._result
 
@@ -238,7 +282,7 @@ class MapResult:
         """Yield results as ordered prefixes become final (per-wave completion events)."""
         if self._n == 0:
             return
-        if self._flags & _abi.FBR_RESULTS_ON_DEVICE:
+        if (self._flags & _abi.FBR_RESULTS_ON_DEVICE) or self._n_items is not None:
             yield from self._wait()
             return
         eng = self._engine
@@ -355,9 +399,11 @@ class Pool:
         self._devices = list(devices) if devices is not None else None
         self._ring_bytes = int(ring_bytes)
         self._timing = bool(timing)
-        if results not in ("host", "device"):
-            raise ValueError("results must be 'host' (pinned result segment) or 'device' (stay in HBM, fetched lazily)")
+        if results not in ("host", "device", "bits"):
+            raise ValueError("results must be 'host' (pinned result segment), 'device' (stay in HBM, fetched lazily) "
+                             "or 'bits' (bool results of range() maps packed 8 to a byte end to end)")
         self._results_on_device = results == "device"
+        self._results_bits = results == "bits"
         self._use_express = bool(express) and not self._error_handling
         self._express_idle_us = int(express_idle_us)
         self._express = None
@@ -441,8 +487,8 @@ class Pool:
             eng.lib.fbr_shared_drop(eng.handle, old)
         return h.value
 
-    def _submit(self, func, enc, kind, chunksize, cls=MapResult, want_sum=True, extra_flags=0):
-        spec = registry.spec(registry.body_name_of(func))
+    def _submit(self, func, enc, kind, chunksize, cls=MapResult, want_sum=True, extra_flags=0, spec=None):
+        spec = spec or registry.spec(registry.body_name_of(func))
         eng = self._engine
         d = _abi.MapDesc()
         d.func_id = spec.func_id
@@ -496,6 +542,14 @@ class Pool:
             iterable = list(iterable)
         spec = self._spec_of(func)
         self.lazy_start_workers(func)
+        if self._results_bits and isinstance(iterable, range) and spec.name in registry.BITS_TWIN:
+            # a bool needs one bit: the twin body computes 8 consecutive indices per result byte, so the
+            # ring, the gather and the D2H copy move n/8 bytes instead of n
+            twin = registry.spec(registry.BITS_TWIN[spec.name])
+            r = self._submit(func, twin.encode_range(iterable), _abi.FBR_MAP, max(1, chunksize // 8), spec=twin)
+            r._n_items, r._user_spec = len(iterable), spec
+            self.sent_tasks += len(iterable) - r._n
+            return r
         return self._submit(func, spec.encode_map(iterable), _abi.FBR_MAP, chunksize)
 
     def map(self, func, iterable, chunksize=None):

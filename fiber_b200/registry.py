@@ -224,6 +224,28 @@ class _UnaryI64(BodySpec):
         return Encoded(len(a), args=a, arg_stride=8)
 
 
+class _Bits8(BodySpec):
+    """``pi_inside_bits8``: task g = the 8 range() indices 8g..8g+7, result = one byte (bit k = index
+    8g+k).  Not bound to a callable: ``Pool(results="bits")`` routes ``map(is_inside, range(n))`` here
+    (``BITS_TWIN``) and presents the bytes as a bit-backed ``ResultArray``."""
+
+    def result_dtype(self):
+        return np.dtype(np.uint8), ()
+
+    def encode_range(self, items):
+        """``range`` of n indices -> ceil(n/8) byte tasks (the body walks the same start/step)."""
+        if not isinstance(items, range):
+            raise TypeError("%s takes range() arguments only" % self.name)
+        if len(items) and not (-2 ** 63 <= items[0] <= 2 ** 63 - 1 and -2 ** 63 <= items[-1] + 7 * items.step <= 2 ** 63 - 1
+                               and -2 ** 63 <= items[-1] <= 2 ** 63 - 1):
+            raise OverflowError("range() bounds exceed the int64 task record")
+        return Encoded((len(items) + 7) // 8, index_start=items.start, index_step=items.step)
+
+
+# bool bodies that have a bit-packed twin: 8 consecutive range() indices per result byte
+BITS_TWIN = {"pi_inside_det": "pi_inside_bits8"}
+
+
 class _BinaryI64(BodySpec):
     """f(x, y) / f(x, y=default) with int arguments: mul2_i64, square_scale_i64."""
 
@@ -389,6 +411,8 @@ def _load_specs():
             s = _Parzen(info, np.float64)
         elif name in ("payload_map_4k", "payload_checksum_4k"):
             s = _Payload4K(info)
+        elif name == "pi_inside_bits8":
+            s = _Bits8(info)
         else:
             s = BodySpec(info)
         specs[name] = s

@@ -54,12 +54,17 @@ typedef enum fbr_result_kind {
     FBR_RES_I64 = 2,     /* int64      (Python int) */
     FBR_RES_U32 = 3,     /* uint32     (Python int) */
     FBR_RES_F64X2 = 4,   /* two float64 (Python tuple of floats) */
-    FBR_RES_NONE = 5     /* body returns None; one pad byte per task */
+    FBR_RES_NONE = 5,    /* body returns None; one pad byte per task */
+    FBR_RES_BITS8 = 6    /* one byte = the bool results of 8 consecutive range() indices, bit k (LSB first)
+                            = index 8*task + k.  A map over N indices is submitted as ceil(N/8) tasks;
+                            the bits past N in the last byte are computed like any other index and are
+                            masked by the caller (fiber_b200/pool.py does) */
 } fbr_result_kind;
 
 #define FBR_BODY_INDEX_ARG 0x1u   /* body can take the task index itself as its int64 argument */
 #define FBR_BODY_NEEDS_SHARED 0x2u /* body reads a shared (broadcast) argument block */
-#define FBR_BODY_SUMMABLE 0x4u    /* gather_ordered can fold sum(results) (bool/int64/u32) */
+#define FBR_BODY_SUMMABLE 0x4u    /* the dispatch kernel can fold sum(results) (bool/int64/u32; popcount for bits) */
+#define FBR_BODY_INDEX_ONLY 0x8u  /* body takes range() arguments only (arg_stride must be 0) */
 
 typedef struct fbr_body_info {
     int32_t func_id;

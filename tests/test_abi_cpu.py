@@ -250,3 +250,27 @@ def test_claim_unit_planning_rules():
     assert all(blocks[i].block_first + blocks[i].block_count == blocks[i + 1].block_first for i in range(7))
     assert all(b.block_first % 32 == 0 for b in blocks)
     assert _abi.load().fbr_plan_query(999, 1, 0, 0, 1, 0, 0, ctypes.byref(_abi.Plan())) == _abi.FBR_EINVAL
+
+
+def test_bits_body_and_bit_backed_result_array():
+    """pi_inside_bits8 is in the body table; a bit-backed ResultArray behaves like the list of bools."""
+    from fiber_b200.pool import ResultArray
+    s = registry.spec("pi_inside_bits8")
+    assert (s.result_bytes, s.result_kind) == (1, _abi.FBR_RES_BITS8)
+    assert s.flags & _abi.FBR_BODY_INDEX_ONLY and s.flags & _abi.FBR_BODY_SUMMABLE
+    assert registry.BITS_TWIN["pi_inside_det"] == "pi_inside_bits8"
+    e = s.encode_range(range(3, 1003, 5))
+    assert (e.n, e.arg_stride, e.index_start, e.index_step) == (25, 0, 3, 5)
+    assert s.encode_range(range(0)).n == 0 and s.encode_range(range(8)).n == 1 and s.encode_range(range(9)).n == 2
+    with pytest.raises(TypeError):
+        s.encode_range([1, 2, 3])
+    rng = np.random.default_rng(5)
+    for n in (1, 7, 8, 9, 1000, 65537):
+        want = rng.integers(0, 2, n).astype(bool)
+        ra = ResultArray(registry.spec("pi_inside_det"), None, None, n=n, bits=np.packbits(want, bitorder="little"))
+        assert len(ra) == n and ra.tolist() == want.tolist() and ra == want.tolist() and ra.sum() == int(want.sum())
+        assert ra[0] == bool(want[0]) and ra[-1] == bool(want[-1]) and ra[n // 2] == bool(want[n // 2])
+        assert ra[1:n - 1] == want[1:n - 1].tolist() and ra[::3] == want[::3].tolist()
+        assert list(ra) == want.tolist() and np.array_equal(np.asarray(ra), want)
+        with pytest.raises(IndexError):
+            ra[n]

@@ -1,6 +1,7 @@
 """GPU parity tests: fiber_b200.Pool (through the C ABI) vs the oracle / the golden vectors produced
 by the real reference pool.  Restates tests/test_pool.py of the reference with the same functions
 and values.  Bit-exact for every integer / byte result; parzen_f32 carries the stated tolerance."""
+import ctypes
 import hashlib
 
 import numpy as np
@@ -549,3 +550,70 @@ def test_express_lane_apply(golden):
     for p in (pool, slow):
         p.terminate()
         p.join()
+
+
+# ---- tests/test_pool.py:317-324 ---------------------------------------------------------------------------
+def test_pool_with_no_argument():
+    # Make sure no exception is raised (the reference maps `print`; here a bound body)
+    p = fiber_b200.Pool()
+    assert p.map(W.identity, [1, 2, 3, 4]) == [1, 2, 3, 4]
+    p.terminate()
+    p.join()
+
+
+# ---- pi body: the ranges the vectorised Philox path treats specially ------------------------------------
+PI_RANGES = [(0, 1, 1), (5, 7, 1), (3, 1001, 7), (-5000, 4097, 3), (2 ** 32 - 100, 333, 1), (2 ** 32 + 50, 97, -3),
+             (10, 65537, 1), (2 ** 33 - 7, 4096 + 15, 1), (-3, 40, 1), (2 ** 40, 5000, 2 ** 31 + 1), (7, 130, -1)]
+
+
+def test_pi_ranges_crossing_word_boundaries(pool):
+    """16 consecutive range() arguments share one Philox round-2 product when their indices share the
+    high 32-bit word; ranges that cross a 2^32 boundary, run backwards or start below zero take the
+    scalar path.  All of them against the plain-C oracle."""
+    from oracle import cref
+    for start, n, step in PI_RANGES:
+        ref, count = cref.pi_inside_range(start, n, step)
+        res = pool.map(W.is_inside, range(start, start + n * step, step))
+        assert len(res) == n and res.sum() == count, (start, n, step)
+        assert np.array_equal(np.asarray(res).view(np.uint8), ref), (start, n, step)
+
+
+def test_bit_packed_results(golden):
+    """Pool(results="bits"): is_inside over a range() comes back one bit per task (pi_inside_bits8), and is
+    the same sequence of bools as the byte-per-task map, the golden vector and the oracle."""
+    from oracle import cref
+    g = golden("pi_inside_det")
+    n = g["n"]
+    pb = fiber_b200.Pool(1, results="bits")
+    res = pb.map(W.is_inside, range(n))
+    assert res.packed is not None and res.packed.nbytes == (n + 7) // 8 and len(res) == n
+    assert res.sum() == g["count"]
+    arr = np.asarray(res)
+    assert arr.dtype == np.bool_ and hashlib.sha256(arr.view(np.uint8).tobytes()).hexdigest() == g["sha256_uint8"]
+    assert res[:256] == [bool(v) for v in g["head_256"]] and res[0] == bool(g["head_256"][0]) and res[-1] == bool(arr[-1])
+    assert res[12345:12399] == arr[12345:12399].tolist() and list(res)[:1000] == arr[:1000].tolist()
+    for start, m, step in PI_RANGES:
+        ref, count = cref.pi_inside_range(start, m, step)
+        r = pb.map(W.is_inside, range(start, start + m * step, step))
+        assert len(r) == m and r.sum() == count, (start, m, step)
+        assert np.array_equal(np.asarray(r).view(np.uint8), ref), (start, m, step)
+        assert np.array_equal(r.packed, np.packbits(ref, bitorder="little")), (start, m, step)   # tail bits are zero
+    # other maps of the same pool are unaffected (non-range arguments, non-bool bodies)
+    assert pb.map(W.is_inside, list(range(100))) == arr[:100].tolist()
+    assert pb.map(W.f, range(10)) == [i * i for i in range(10)]
+    assert list(pb.imap(W.is_inside, range(1000))) == arr[:1000].tolist()
+    # 1e8 indices: 12.5 MB cross PCIe instead of 100 MB; count and a strided sample against the oracle
+    big = pb.map(W.is_inside, range(10 ** 8))
+    assert big.packed.nbytes == 12_500_000 and big.sum() == 78540462
+    ref, _ = cref.pi_inside_range(0, 10 ** 8, 1)
+    assert np.array_equal(big.packed, np.packbits(ref, bitorder="little"))
+    # the raw body refuses explicit argument records
+    lib, spec = _abi.load(), fiber_b200.registry.spec("pi_inside_bits8")
+    d = _abi.MapDesc()
+    d.func_id, d.n_tasks, d.arg_stride = spec.func_id, 4, 8
+    buf = np.zeros(4, np.int64)
+    d.args = buf.ctypes.data
+    seq = ctypes.c_uint64()
+    assert lib.fbr_map_submit(pb._engine.handle, ctypes.byref(d), ctypes.byref(seq)) == _abi.FBR_EINVAL
+    pb.terminate()
+    pb.join()
