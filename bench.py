@@ -52,6 +52,19 @@ def load_peaks():
         return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback (B200_PROFILING.md)"
 
 
+def load_imad_peak():
+    """Measured IMAD.WIDE.U32 rate of this GPU model (profiles/microbench/imad_peak.cu, committed summary)."""
+    path = os.path.join(ROOT, "profiles", "r01_imad_peak.json")
+    try:
+        with open(path) as fh:
+            d = json.load(fh)
+        best = max(v["Gops"] for k, v in d.items() if k.startswith("imad_wide_u32"))
+        body = max(v["tasks_per_s"] for k, v in d.items() if k.startswith("pi_body_screened"))
+        return {"gops": best, "source": "profiles/r01_imad_peak.json (measured)", "pi_body_screened_tasks_per_s": "%.3g" % body}
+    except (OSError, ValueError, KeyError):
+        return {"gops": None, "source": "unavailable", "pi_body_screened_tasks_per_s": "n/a"}
+
+
 def load_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
     capture of profiles/prof_target.py (same kernels, same sizes); newest round wins."""
@@ -487,6 +500,12 @@ def run_multi_gpu(args, dist, dev):
 
 
 # ------------------------------------------------------------------------------------------------
+def cref_count_first_1e6(first):
+    """Oracle count of is_inside over [first, first + 1e6) (checker only)."""
+    from oracle import cref
+    return cref.pi_inside_range(first, 10 ** 6, want_array=False)[1]
+
+
 def run_ours(args, dist):
     import numpy as np
     import fiber_b200
@@ -544,18 +563,22 @@ def run_ours(args, dist):
                 "traffic": traffic_of("gather_rows_kernel@prof_pi"), "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": gather_bytes, "avg_launch_ms": gather_ms,
                 "note": "2*R*N bytes (R=1 B) per launch; the ring was just written by the dispatch kernel so part of the reads can hit L2"}
-    # Philox4x32-10 + f64 compare: ~20 IMAD.WIDE-class multiplies + ~60 ALU ops per task; the bound
-    # is the SM integer pipes, not HBM (1 B written per task).
-    sm_clock = float(peaks.get("sm_max_mhz", 1965.0)) * 1e6
-    int_peak = 148 * 128 * sm_clock / 1e12          # lane-ops/s, all SMs, 128 lanes/clk
-    roofline_dispatch = {"kernel": "dispatch_thread_kernel<PiInsideDet, index args> (+ sum fold)", "bound": "alu",
+    # Philox4x32-10 + circle test: the bound is the SM's integer-multiply pipe (IMAD.WIDE.U32), not HBM
+    # (1 B written per task).  Its peak is measured, not nominal: profiles/microbench/imad_peak.cu.
+    wide_per_task = 18
+    imad = load_imad_peak()
+    wide_rate = wide_per_task * PI_TASKS / (dispatch_ms * 1e-3)
+    roofline_dispatch = {"kernel": "dispatch_thread_kernel<PiInsideDet, index args> (+ sum fold)", "bound": "alu (IMAD.WIDE.U32 pipe)",
                          "avg_launch_ms": dispatch_ms, "tasks_per_s": PI_TASKS / (dispatch_ms * 1e-3),
                          "hbm_gbs": PI_TASKS * 1 / (dispatch_ms * 1e-3) / 1e9,
-                         "imad_wide_per_task": 21,
-                         "fmaheavy_frac_ncu": 0.736,
-                         "note": "bound by the integer-multiply pipe: Philox4x32-10 needs 20 IMAD.WIDE.U32 per task (+1 for the "
-                                 "index), ~4 fmaheavy cycles each; ncu (profiles/r01_ncu_kernels.csv) shows fmaheavy 73.6 % "
-                                 "active, dram 1.5 %"}
+                         "imad_wide_per_task": wide_per_task,
+                         "achieved": wide_rate / 1e9, "peak": imad.get("gops"), "unit": "G IMAD.WIDE.U32/s",
+                         "frac": (wide_rate / 1e9 / imad["gops"]) if imad.get("gops") else None,
+                         "peak_source": imad.get("source"),
+                         "note": "Philox4x32-10 on a (lo, hi, 0, 0) counter: 18 32x32->64 multiplies per task (round 1 has a "
+                                 "zero word, round 2's M0*(hi^key) is shared by 16 tasks); circle test screened in fp32, "
+                                 "float64 only within 2^-19 of the circle; the same body alone (no ring traffic) reaches "
+                                 "%s tasks/s in the microbenchmark" % imad.get("pi_body_screened_tasks_per_s")}
     eng.dfree(out_dev)
 
     # ---------------- secondary: 4 KB payload map, device resident ----------------------------------
@@ -700,6 +723,36 @@ def run_ours(args, dist):
     launches_e2e += sd["dispatch_launches"] + sd["gather_launches"]
     dpool.terminate()
     dpool.join()
+    # secondary e2e: same call on Pool(results="bits") -- a bool travels as one bit (pi_inside_bits8):
+    # the ordered, bit-packed results of all 1e8 tasks reach the pinned host segment every step
+    bpool = fiber_b200.Pool(1, devices=[dev], results="bits")
+    bit_counts = []
+
+    def e2e_bits_step():
+        res = bpool.map(W.is_inside, my_range)
+        c = res.sum()
+        bit_counts.append(dist.sum_i64(c) if world > 1 else c)
+        e2e_bits_step.last = res
+
+    for _ in range(3):
+        e2e_bits_step()
+    bpool.reset_stats()
+    t_e2e_bits = timed_steps(dist, args.steps, 0, e2e_bits_step, None, clocks.windows)
+    sb = bpool.stats()
+    packed = e2e_bits_step.last.packed
+    e2e["results_bit_packed"] = {"value": world * PI_TASKS * args.steps / t_e2e_bits, "unit": "tasks/s",
+                                 "ms_per_step": 1e3 * t_e2e_bits / args.steps,
+                                 "h2d_bytes_per_step": sb["h2d_bytes"] // args.steps, "d2h_bytes_per_step": sb["d2h_bytes"] // args.steps,
+                                 "api": "fiber_b200.Pool(1, results='bits').map(is_inside_det, range(1e8)) -> pinned bit-packed ResultArray + count",
+                                 "count": bit_counts[-1], "packed_bytes": int(packed.nbytes),
+                                 "parity_spot_check": bool(int(np.unpackbits(packed[:125000], bitorder="little").sum()) ==
+                                                           cref_count_first_1e6(my_first)),
+                                 "note": "secondary figure: same ordered bool results, 1 bit per task on the host (ResultArray unpacks on access)"}
+    launches_e2e += sb["dispatch_launches"] + sb["gather_launches"]
+    e2e_bits_step.last = None
+    del packed
+    bpool.terminate()
+    bpool.join()
 
     # T_list at 1e6: Python list in hand, the reference's own end point
     t0 = time.perf_counter()
