@@ -147,6 +147,8 @@ class Dist:
             self.torch, self.dist = torch, dist
             if backend == "nccl":
                 torch.cuda.set_device(self.local_rank)
+                if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+                    os.environ["NCCL_DEBUG"] = "WARN"     # keep NCCL's version banner off stdout: one JSON line only
             dist.init_process_group(backend=backend)
         if want_gpus != self.world and self.world > 1:
             raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (want_gpus, self.world))
@@ -247,15 +249,15 @@ def timed_steps(dist, steps, warmup, step_fn, drain_fn=None, clock_windows=None)
         step_fn()
     if drain_fn:
         drain_fn()
-    dist.barrier()
+    dist.barrier()                 # every rank starts its K steps together (barrier + device sync)
     t0 = time.perf_counter()
     for _ in range(steps):
         step_fn()
     if drain_fn:
-        drain_fn()
-    dist.barrier()
+        drain_fn()                 # blocks until this rank's last step is complete on the device
     t1 = time.perf_counter()
-    if clock_windows is not None:
+    dist.barrier()                 # closing bracket; its own latency (an NCCL all-reduce) is not part of the K steps:
+    if clock_windows is not None:  # the job's time is the slowest rank's, taken by the max below
         clock_windows.append((t0, t1))
     return dist.max(t1 - t0)
 

@@ -17,6 +17,12 @@ n = 300_017
 res = pool.map(W.is_inside, range(n))
 ref, count = cref.pi_inside_range(0, n)
 assert res.sum() == count and np.array_equal(np.asarray(res).view(np.uint8), ref)
+bp = fiber_b200.Pool(1, results="bits", ring_bytes=1 << 20)                                          # pi_inside_bits8
+rb = bp.map(W.is_inside, range(n))
+assert rb.sum() == count and np.array_equal(rb.packed, np.packbits(ref, bitorder="little"))
+r32, c32 = cref.pi_inside_range(2 ** 32 - 1000, 5003, 1)                                                # 2^32 crossing: scalar path
+assert np.array_equal(np.asarray(pool.map(W.is_inside, range(2 ** 32 - 1000, 2 ** 32 + 4003))).view(np.uint8), r32)
+assert np.array_equal(bp.map(W.is_inside, range(2 ** 32 - 1000, 2 ** 32 + 4003)).packed, np.packbits(r32, bitorder="little"))
 recs = cref.payload_records(0, 700)
 assert np.array_equal(np.asarray(pool.map(W.payload_map, recs)), cref.payload_map(0, recs))           # TMA dispatch + TMA gather
 assert np.array_equal(np.asarray(pool.map(W.payload_map, recs, 7)), cref.payload_map(0, recs))        # odd units

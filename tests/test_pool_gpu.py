@@ -617,3 +617,21 @@ def test_bit_packed_results(golden):
     assert lib.fbr_map_submit(pb._engine.handle, ctypes.byref(d), ctypes.byref(seq)) == _abi.FBR_EINVAL
     pb.terminate()
     pb.join()
+
+
+def test_chunk_size_blocking_tasks_run_concurrently():
+    """tests/test_pool.py:179-234 pins that with chunksize=1 nine *blocking* tasks occupy nine workers at once
+    (a chunk computed wrong would queue one behind another and the test would hang).  Here a worker slot is a
+    persistent CTA and a claim unit of a blocking body is one task: nine 0.25 s tasks take 0.25 s, not 2.25 s."""
+    import time
+    pool = fiber_b200.Pool(1)
+    assert pool.map(W.sleep_worker, [0.001] * 3, chunksize=1) == [None] * 3         # start workers, load the kernel
+    t0 = time.perf_counter()
+    res = pool.map(W.sleep_worker, [0.25] * 9, chunksize=1)
+    dt = time.perf_counter() - t0
+    assert res == [None] * 9 and 0.25 <= dt < 0.75, dt
+    t0 = time.perf_counter()
+    res = pool.map(W.sleep_worker, [0.05] * 64)                                       # default chunksize: still one task per unit
+    assert res == [None] * 64 and time.perf_counter() - t0 < 0.5
+    pool.terminate()
+    pool.join()
