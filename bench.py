@@ -147,8 +147,8 @@ class Dist:
             self.torch, self.dist = torch, dist
             if backend == "nccl":
                 torch.cuda.set_device(self.local_rank)
-                if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-                    os.environ["NCCL_DEBUG"] = "WARN"     # keep NCCL's version banner off stdout: one JSON line only
+                # NCCL writes its version banner / warnings to stdout; rank 0's stdout carries ONE JSON line
+                os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
             dist.init_process_group(backend=backend)
         if want_gpus != self.world and self.world > 1:
             raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (want_gpus, self.world))
