@@ -102,3 +102,30 @@ def test_concurrent_submitters_share_one_pool():
     assert not errors, errors[:1]
     pool.terminate()
     pool.join()
+
+
+@pytest.mark.parametrize("ring_kib", [64, 4096])
+def test_random_pi_ranges_bytes_and_bits(ring_kib):
+    """Random range(start, stop, step) maps of the pi body through both result layouts (one byte / one bit per
+    task) against the plain-C oracle: starts around 0, 2^32 and 2^40, negative and large steps, lengths that
+    leave partial vectors, partial bytes and partial claim units, small rings (many waves)."""
+    rng = np.random.default_rng(99 + ring_kib)
+    pools = [fiber_b200.Pool(1, ring_bytes=ring_kib << 10), fiber_b200.Pool(1, ring_bytes=ring_kib << 10, results="bits")]
+    try:
+        for trial in range(30):
+            n = int(rng.choice([1, 7, 8, 9, 15, 16, 17, 127, 4095, 4096, 4097, 32769, int(rng.integers(1, 200000))]))
+            anchor = int(rng.choice([0, 2 ** 32, 2 ** 40, -2 ** 33]))
+            start = anchor + int(rng.integers(-70000, 70000))
+            step = int(rng.choice([1, 1, 2, 5, -1, -3, 2 ** 31 + 7, 2 ** 20]))
+            cs = int(rng.choice([1, 8, 32, 100, 5000]))
+            ref, count = cref.pi_inside_range(start, n, step)
+            r = range(start, start + n * step, step)
+            for pool in pools:
+                res = pool.map(W.is_inside, r, cs)
+                assert len(res) == n and res.sum() == count, (start, n, step, cs)
+                assert np.array_equal(np.asarray(res).view(np.uint8), ref), (start, n, step, cs)
+            assert np.array_equal(res.packed, np.packbits(ref, bitorder="little")), (start, n, step, cs)
+    finally:
+        for pool in pools:
+            pool.terminate()
+            pool.join()
