@@ -147,9 +147,20 @@ class Dist:
             self.torch, self.dist = torch, dist
             if backend == "nccl":
                 torch.cuda.set_device(self.local_rank)
-                # NCCL writes its version banner / warnings to stdout; rank 0's stdout carries ONE JSON line
-                os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-            dist.init_process_group(backend=backend)
+            # NCCL prints its version banner on stdout when the first communicator is created; rank 0's stdout
+            # carries ONE JSON line, so fd 1 points at stderr until that has happened
+            sys.stdout.flush()
+            saved = os.dup(1)
+            os.dup2(2, 1)
+            try:
+                dist.init_process_group(backend=backend)
+                dist.barrier()
+                if backend == "nccl":
+                    torch.cuda.synchronize()
+            finally:
+                sys.stdout.flush()
+                os.dup2(saved, 1)
+                os.close(saved)
         if want_gpus != self.world and self.world > 1:
             raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (want_gpus, self.world))
 
