@@ -127,6 +127,23 @@ def pi_inside_det_np(start, stop, step=1):
 # ----------------------------------------------------------------------------------------------
 
 
+def pi_inside_bits8(g, start=0, step=1):
+    """Body ``pi_inside_bits8`` (include/fiber_b200.h, FBR_RES_BITS8): the bool results of the 8 range()
+    indices ``8g .. 8g+7`` of ``range(start, ..., step)`` in one byte, bit k (LSB first) = index 8g+k.
+    Same per-index function as ``pi_inside_det`` (examples/pi_estimation.py:9-11): only the result layout
+    differs, the reference's list of bools is ``unpackbits(bytes, bitorder="little")[:n]``."""
+    b = 0
+    for k in range(8):
+        b |= int(pi_inside_det(start + (8 * g + k) * step)) << k
+    return b
+
+
+def pi_inside_bits_np(start, n, step=1):
+    """The ``ceil(n/8)`` result bytes of a bit-packed map over ``range(start, start + n*step, step)``, bits past
+    ``n`` cleared (what ``fiber_b200.Pool(results="bits")`` hands back as ``ResultArray.packed``)."""
+    return np.packbits(pi_inside_det_np(start, start + n * step, step), bitorder="little")
+
+
 def parzen_estimation(x_samples, point_x, h):
     """Restatement of examples/parzen_estimation.py:6-15 (hypercube Parzen window).
 

@@ -181,3 +181,15 @@ def test_chunk_plan_and_placement():
     inv = Z.Inventory(lambda: next(it))
     assert inv.add(n) == 1
     assert inv.get(1) == vals.tolist()
+
+
+def test_pi_bits8_restatement_matches_the_byte_body(golden):
+    """pi_inside_bits8 is pi_inside_det in another result layout: pinned by the same golden vector."""
+    g = golden("pi_inside_det")
+    head = np.array(g["head_256"], dtype=np.uint8)
+    assert [B.pi_inside_bits8(j) for j in range(32)] == np.packbits(head, bitorder="little").tolist()
+    arr, _ = cref.pi_inside_range(-17, 1003, step=3)
+    packed = B.pi_inside_bits_np(-17, 1003, 3)
+    assert packed.nbytes == 126 and np.array_equal(np.unpackbits(packed, bitorder="little")[:1003], arr)
+    assert [B.pi_inside_bits8(j, -17, 3) for j in range(125)] == packed[:125].tolist()     # full bytes
+    assert packed[125] == B.pi_inside_bits8(125, -17, 3) & 0b111                             # 1003 = 125*8 + 3

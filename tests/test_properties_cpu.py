@@ -34,7 +34,7 @@ def test_block_partition_invariants(n, world, align):
 
 
 @settings(max_examples=300, deadline=None)
-@given(st.sampled_from(["pi_inside_det", "square_i64", "mul2_i64", "payload_map_4k", "payload_checksum_4k", "parzen_f64"]),
+@given(st.sampled_from(["pi_inside_det", "pi_inside_bits8", "square_i64", "mul2_i64", "payload_map_4k", "payload_checksum_4k", "parzen_f64"]),
        st.integers(1, 10 ** 9), st.integers(0, 100000), st.sampled_from([64 << 10, 1 << 20, 256 << 20, 4 << 30]),
        st.integers(1, 8))
 def test_claim_unit_invariants(body, n, cs, ring, nw):
