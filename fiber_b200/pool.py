@@ -121,7 +121,7 @@ class ResultArray(collections.abc.Sequence):
 
     @property
     def on_device(self):
-        return self._arr is None
+        return self._arr is None and self._bits is None
 
     def __len__(self):
         return self._n
@@ -173,7 +173,7 @@ class ResultArray(collections.abc.Sequence):
         head = self[:6]
         return "ResultArray(%s%s, len=%d, body=%s%s)" % (head, "..." if n > 6 else "", n, self._spec.name,
                                                          ", bit-packed" if self._bits is not None else
-                                                         ", on device" if self._arr is None else "")
+                                                         ", on device" if self.on_device else "")
 
     def __array__(self, dtype=None, copy=None):
         a = self._a
