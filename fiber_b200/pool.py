@@ -282,10 +282,28 @@ class MapResult:
         """Yield results as ordered prefixes become final (per-wave completion events)."""
         if self._n == 0:
             return
-        if (self._flags & _abi.FBR_RESULTS_ON_DEVICE) or self._n_items is not None:
+        if self._flags & _abi.FBR_RESULTS_ON_DEVICE:
             yield from self._wait()
             return
         eng = self._engine
+        if self._n_items is not None:
+            # bit-packed map: progress is counted in result bytes (8 tasks each); every byte of a finished
+            # wave is a full byte, the (masked) last byte of the map only comes from _wait()
+            done, emitted = ctypes.c_uint64(0), 0
+            while emitted < self._n:
+                _abi.check(eng.lib.fbr_result_poll(eng.handle, self._seq, ctypes.byref(done)))
+                if done.value >= self._n:
+                    break
+                if done.value > emitted:
+                    part = self._peek(emitted, done.value, np.dtype(np.uint8), ())
+                    yield from np.unpackbits(part, bitorder="little").view(np.bool_).tolist()
+                    emitted = done.value
+                else:
+                    time.sleep(0.0002)
+            res = self._wait()
+            if emitted * 8 < self._n_items:
+                yield from res[emitted * 8:]
+            return
         done = ctypes.c_uint64(0)
         emitted = 0
         dtype, sub = self._spec.result_dtype()

@@ -602,6 +602,14 @@ def test_bit_packed_results(golden):
     assert pb.map(W.is_inside, list(range(100))) == arr[:100].tolist()
     assert pb.map(W.f, range(10)) == [i * i for i in range(10)]
     assert list(pb.imap(W.is_inside, range(1000))) == arr[:1000].tolist()
+    small = fiber_b200.Pool(1, results="bits", ring_bytes=64 << 10)      # many waves: imap streams byte prefixes
+    m = 700_003
+    it = small.imap(W.is_inside, range(m))
+    first = [next(it) for _ in range(10)]
+    assert first == arr[:10].tolist() and first + list(it) == arr[:m].tolist()
+    assert sorted(small.imap_unordered(W.is_inside, range(5, 5 + 4099))) == sorted(arr[5:5 + 4099].tolist())
+    small.terminate()
+    small.join()
     # 1e8 indices: 12.5 MB cross PCIe instead of 100 MB; count and a strided sample against the oracle
     big = pb.map(W.is_inside, range(10 ** 8))
     assert big.packed.nbytes == 12_500_000 and big.sum() == 78540462
