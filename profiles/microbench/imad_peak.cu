@@ -80,6 +80,28 @@ __global__ void __launch_bounds__(256) k_pi_screen(uint32_t* out, int iters, uin
     if (acc == 0x12345u || dmin == 0.123f) out[0] = acc;
 }
 
+// the same with the screens of two tasks evaluated by packed FP32 instructions (FADD2 / FFMA2)
+__global__ void __launch_bounds__(256) k_pi_screen2(uint32_t* out, int iters, uint32_t seed) {
+    uint32_t acc = 0;
+    uint32_t base = seed + (blockIdx.x * 256u + threadIdx.x) * 16u;
+    const uint32_t hx = 0u ^ 0xF1BE5EEDu;
+    const uint2 hk = make_uint2(__umulhi(0xD2511F53u, hx), 0xD2511F53u * hx);
+    float dmin = 1.0f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int v = 0; v < 16; v += 2) {
+            uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
+            philox_block_lo(base + v, hk, a0, a1, a2, a3);
+            philox_block_lo(base + v + 1, hk, b0, b1, b2, b3);
+            float da, db;
+            pi_screen2(a0, a2, b0, b2, da, db, dmin);
+            acc += (da < 0.0f ? 1u : 0u) + (db < 0.0f ? 1u : 0u);
+        }
+        base += gridDim.x * 4096u;
+    }
+    if (acc == 0x12345u || dmin == 0.123f) out[0] = acc;
+}
+
 template <class F>
 static float time_ms(F launch) {
     cudaEvent_t a, b;
@@ -126,6 +148,9 @@ int main() {
                tasks / (ms * 1e-3), tasks * 18 / (ms * 1e-3) / sms / (clk_khz * 1e3));
         ms = time_ms([&] { k_pi_screen<<<grid, 256>>>(out, it2, 1u); });
         printf(",\n \"pi_body_screened_occ%d\": {\"ms\": %.4f, \"tasks_per_s\": %.4e, \"wide_mul_per_clk_per_sm\": %.2f}", occ, ms,
+               tasks / (ms * 1e-3), tasks * 18 / (ms * 1e-3) / sms / (clk_khz * 1e3));
+        ms = time_ms([&] { k_pi_screen2<<<grid, 256>>>(out, it2, 1u); });
+        printf(",\n \"pi_body_screened_f32x2_occ%d\": {\"ms\": %.4f, \"tasks_per_s\": %.4e, \"wide_mul_per_clk_per_sm\": %.2f}", occ, ms,
                tasks / (ms * 1e-3), tasks * 18 / (ms * 1e-3) / sms / (clk_khz * 1e3));
     }
     printf("\n}\n");
