@@ -98,6 +98,20 @@ def child():
                + [-3, -2, -1] + [2 ** 63 - 1, -(2 ** 63)])
     pi["special_args"] = special
     pi["special_results"] = [int(r) for r in pool.map(B.pi_inside_det, special)]
+    # ranges the GPU's vectorised Philox path treats specially (16 consecutive arguments share one round-2
+    # product while their indices share the high 32-bit word): 2^32 crossings, negative starts, backward and
+    # large steps, lengths that leave partial vectors / partial bytes.  sha256 of the uint8 results and of the
+    # same results packed 8 to a byte (LSB first; the layout of Pool(results="bits")).
+    cases = [(0, 1, 1), (5, 7, 1), (3, 1001, 7), (-5000, 4097, 3), (2 ** 32 - 100, 333, 1), (2 ** 32 + 50, 97, -3),
+             (10, 65537, 1), (2 ** 33 - 7, 4096 + 15, 1), (-3, 40, 1), (2 ** 40, 5000, 2 ** 31 + 1), (7, 130, -1)]
+    pi["range_cases"] = []
+    for start, m, step in cases:
+        r = np.array(pool.map(B.pi_inside_det, range(start, start + m * step, step)), dtype=np.uint8)
+        assert len(r) == m
+        pi["range_cases"].append({"start": start, "n": m, "step": step, "count": int(r.sum()),
+                                  "sha256_uint8": _sha(r.tobytes()),
+                                  "sha256_bits_le": _sha(np.packbits(r, bitorder="little").tobytes())})
+    pi["sha256_bits_le"] = _sha(np.packbits(arr, bitorder="little").tobytes())
     pi["uniforms_p0_hex"] = [v.hex() for v in B.pi_uniforms(0)]
     pi["uniforms_p12345_hex"] = [v.hex() for v in B.pi_uniforms(12345)]
 

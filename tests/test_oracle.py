@@ -193,3 +193,20 @@ def test_pi_bits8_restatement_matches_the_byte_body(golden):
     assert packed.nbytes == 126 and np.array_equal(np.unpackbits(packed, bitorder="little")[:1003], arr)
     assert [B.pi_inside_bits8(j, -17, 3) for j in range(125)] == packed[:125].tolist()     # full bytes
     assert packed[125] == B.pi_inside_bits8(125, -17, 3) & 0b111                             # 1003 = 125*8 + 3
+
+
+def test_pi_range_cases_from_the_reference_pool(golden):
+    """Ranges crossing 2^32, negative starts, backward / large steps: the C oracle and the NumPy restatement
+    against what the real reference pool returned (tests/golden/make_golden.py), bytes and packed bits."""
+    import hashlib
+    g = golden("pi_inside_det")
+    assert len(g["range_cases"]) >= 11
+    for c in g["range_cases"]:
+        arr, count = cref.pi_inside_range(c["start"], c["n"], c["step"])
+        assert count == c["count"] and hashlib.sha256(arr.tobytes()).hexdigest() == c["sha256_uint8"], c
+        assert hashlib.sha256(np.packbits(arr, bitorder="little").tobytes()).hexdigest() == c["sha256_bits_le"], c
+        if c["n"] <= 5000:
+            assert np.array_equal(B.pi_inside_det_np(c["start"], c["start"] + c["n"] * c["step"], c["step"]), arr), c
+            assert np.array_equal(B.pi_inside_bits_np(c["start"], c["n"], c["step"]), np.packbits(arr, bitorder="little")), c
+    full, _ = cref.pi_inside_range(0, g["n"])
+    assert hashlib.sha256(np.packbits(full, bitorder="little").tobytes()).hexdigest() == g["sha256_bits_le"]

@@ -566,16 +566,26 @@ PI_RANGES = [(0, 1, 1), (5, 7, 1), (3, 1001, 7), (-5000, 4097, 3), (2 ** 32 - 10
              (10, 65537, 1), (2 ** 33 - 7, 4096 + 15, 1), (-3, 40, 1), (2 ** 40, 5000, 2 ** 31 + 1), (7, 130, -1)]
 
 
-def test_pi_ranges_crossing_word_boundaries(pool):
+def test_pi_ranges_crossing_word_boundaries(pool, golden):
     """16 consecutive range() arguments share one Philox round-2 product when their indices share the
     high 32-bit word; ranges that cross a 2^32 boundary, run backwards or start below zero take the
-    scalar path.  All of them against the plain-C oracle."""
+    scalar path.  All of them against the plain-C oracle and against what the real reference pool returned
+    for the same ranges (golden range_cases)."""
     from oracle import cref
     for start, n, step in PI_RANGES:
         ref, count = cref.pi_inside_range(start, n, step)
         res = pool.map(W.is_inside, range(start, start + n * step, step))
         assert len(res) == n and res.sum() == count, (start, n, step)
         assert np.array_equal(np.asarray(res).view(np.uint8), ref), (start, n, step)
+    bits = fiber_b200.Pool(1, results="bits")
+    for c in golden("pi_inside_det")["range_cases"]:
+        r = range(c["start"], c["start"] + c["n"] * c["step"], c["step"])
+        res = pool.map(W.is_inside, r)
+        assert res.sum() == c["count"] and hashlib.sha256(np.asarray(res).view(np.uint8).tobytes()).hexdigest() == c["sha256_uint8"], c
+        rb = bits.map(W.is_inside, r)
+        assert rb.sum() == c["count"] and hashlib.sha256(rb.packed.tobytes()).hexdigest() == c["sha256_bits_le"], c
+    bits.terminate()
+    bits.join()
 
 
 def test_bit_packed_results(golden):
@@ -587,7 +597,7 @@ def test_bit_packed_results(golden):
     pb = fiber_b200.Pool(1, results="bits")
     res = pb.map(W.is_inside, range(n))
     assert res.packed is not None and res.packed.nbytes == (n + 7) // 8 and len(res) == n
-    assert res.sum() == g["count"]
+    assert res.sum() == g["count"] and hashlib.sha256(res.packed.tobytes()).hexdigest() == g["sha256_bits_le"]
     arr = np.asarray(res)
     assert arr.dtype == np.bool_ and hashlib.sha256(arr.view(np.uint8).tobytes()).hexdigest() == g["sha256_uint8"]
     assert res[:256] == [bool(v) for v in g["head_256"]] and res[0] == bool(g["head_256"][0]) and res[-1] == bool(arr[-1])
