@@ -2,7 +2,7 @@
 """bench.py -- Pool.map tasks/sec on B200 (BASELINE.json metric), one JSON line on rank 0.
 
     python bench.py --gpus 1 --steps 10 --warmup 3            # this repo's arm
-    python bench.py --impl reference --steps 3 --warmup 1     # CPU arm (oracle port of ZPool)
+    python bench.py --impl reference --steps 3 --warmup 1     # CPU arm: the reference's own ZPool
     torchrun ... bench.py --gpus N ...                        # one rank per GPU
 
 A "step" is one pass of the hot path over one batch of synthetic tasks:
@@ -12,21 +12,29 @@ A "step" is one pass of the hot path over one batch of synthetic tasks:
   (weak scaling, the map shards by index block with no data-path collective; the scalar count is
   summed over ranks with one NCCL all-reduce per step when N > 1).
   - ``value``  : whole-job tasks/s with everything resident in HBM (index arguments need no input
-                 bytes; ordered uint8 results + int64 count stay on the device).
-  - ``e2e``    : the same through the reference-facing call ``fiber_b200.Pool.map`` -- task records
-                 H2D from the pinned task ring, ordered results D2H into the pinned result segment,
+                 bytes; ordered uint8 results + int64 count stay on the device).  A contiguous map is
+                 placed directly at its final index by the dispatch kernel (one launch per step).
+  - ``e2e``    : the same through the reference-facing call ``fiber_b200.Pool.map`` -- ordered results
+                 D2H into the pinned result segment (bool results travel one bit each by default),
                  count read on the host -- all inside the timed region.
-* secondary workload ``synthetic 4 KB-payload map, 1e6 tasks`` (configs[3], per GPU): the HBM-bound
-  pair dispatch_payload_map + gather_ordered, reported under ``payload4k``.
+  - ``roofline``: the result-gather kernel the north-star names (gather_ordered), timed live with CUDA
+                 events on the engine's compute stream (FBR_POOL_TIMING) in a leg where it has to run:
+                 the same 1e8-task map with task records shuffled inside each wave, so ring (arrival)
+                 order != index order and every unit is placed by its header.
+* ``parzen``   : BASELINE.json configs[2] -- 102 window widths via apply_async (as the example) and via
+                 starmap(chunksize=1), kernel time, L2 read rate, fp32 boundary mismatches, CPU time.
+* ``payload4k``: ``synthetic 4 KB-payload map, 1e6 tasks`` (configs[3], per GPU): the HBM-bound kernels at
+                 8.2 GB per launch (dispatch_payload_map_tma, gather_bulk).
 
-``roofline`` is the result-gather kernel the north-star names (gather_ordered), measured live with
-CUDA events on the engine's compute stream (FBR_POOL_TIMING) against MEASURED_PEAKS.json's HBM copy
-bandwidth; ``roofline_dispatch`` says what bounds the pi dispatch kernel (integer ALU, not HBM).
-``cpu_baseline`` times oracle/zpool_port.py (CPU port of the reference ZPool, real processes + zmq)
-on a bounded sample on this box's host cores.
+``cpu_baseline`` / ``--impl reference`` time the UNMODIFIED reference pool (``baseline/_ref/fiber``: a
+git-ignored copy of /root/reference/fiber made by ``__graft_entry__.build()`` with the one constant
+``socket_lib = "nanomsg" -> "zmq"`` flipped because nnpy is not installable offline) on this box's host
+cores; if that copy is missing or fails, the oracle port of ZPool (``oracle/zpool_port.py``) stands in
+and the line says ``kind: "port"``.
 """
 import argparse
 import ctypes
+import hashlib
 import json
 import os
 import statistics
@@ -41,6 +49,7 @@ sys.path.insert(0, ROOT)
 PI_TASKS = 10 ** 8
 PAYLOAD_TASKS = 10 ** 6
 CPU_SAMPLE_TASKS = 10 ** 6
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
 
 
 def load_peaks():
@@ -52,28 +61,33 @@ def load_peaks():
         return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback (B200_PROFILING.md)"
 
 
+def _newest(pattern):
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", pattern)))
+    return files[-1] if files else None
+
+
 def load_imad_peak():
     """Measured IMAD.WIDE.U32 rate of this GPU model (profiles/microbench/imad_peak.cu, committed summary)."""
-    path = os.path.join(ROOT, "profiles", "r01_imad_peak.json")
+    path = _newest("r*_imad_peak.json")
     try:
         with open(path) as fh:
             d = json.load(fh)
         best = max(v["Gops"] for k, v in d.items() if k.startswith("imad_wide_u32"))
         body = max(v["tasks_per_s"] for k, v in d.items() if k.startswith("pi_body_screened"))
-        return {"gops": best, "source": "profiles/r01_imad_peak.json (measured)", "pi_body_screened_tasks_per_s": "%.3g" % body}
-    except (OSError, ValueError, KeyError):
+        return {"gops": best, "source": os.path.relpath(path, ROOT) + " (measured)", "pi_body_screened_tasks_per_s": "%.3g" % body}
+    except (OSError, ValueError, KeyError, TypeError):
         return {"gops": None, "source": "unavailable", "pi_body_screened_tasks_per_s": "n/a"}
 
 
 def load_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
-    capture of profiles/prof_target.py (same kernels, same sizes); newest round wins."""
-    import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
-    if not files:
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch (and the capture's commit) from the committed
+    `ncu --set full` capture of profiles/prof_target.py (same kernels, same sizes); newest round wins."""
+    path = _newest("r*_traffic.json")
+    if not path:
         return {}, None
-    with open(files[-1]) as fh:
-        return json.load(fh), os.path.relpath(files[-1], ROOT)
+    with open(path) as fh:
+        return json.load(fh), os.path.relpath(path, ROOT)
 
 
 class ClockSampler:
@@ -132,6 +146,34 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+class NvlinkCounters:
+    """NVML per-GPU NVLink payload counters (KiB, all links): bytes sent / received by one GPU over a region."""
+
+    def __init__(self, gpu_index):
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.read()
+        except Exception:
+            self.h = None
+
+    def read(self):
+        if self.h is None:
+            return None
+        nv = self.nv
+        vals = nv.nvmlDeviceGetFieldValues(self.h, [(nv.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, 0xFFFFFFFF),
+                                                    (nv.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX, 0xFFFFFFFF)])
+        out = []
+        for v in vals:
+            if v.nvmlReturn != 0:
+                return None
+            out.append(int(v.value.ullVal) * 1024)
+        return tuple(out)     # (tx bytes, rx bytes)
+
+
 # ------------------------------------------------------------------------------------------------
 # distributed plumbing (torch.distributed is plumbing only: barrier, max-reduce, count all-reduce)
 # ------------------------------------------------------------------------------------------------
@@ -186,6 +228,9 @@ class Dist:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
         return int(t.item())
 
+    def all_true(self, flag):
+        return self.sum_i64(0 if flag else 1) == 0
+
     def finish(self):
         if self.world > 1:
             self.dist.destroy_process_group()
@@ -212,17 +257,24 @@ class RawEngine:
     def dfree(self, p):
         self.lib.fbr_device_free(self.h, 0, p)
 
-    def submit(self, body, n, out_dev, args_dev=None, arg_stride=0, index_start=0, task_base=0, want_sum=True):
+    def d2h(self, dptr, nbytes, offset=0):
+        import numpy as np
+        host = np.empty(nbytes, dtype=np.uint8)
+        self.abi.check(self.lib.fbr_memcpy_d2h(self.h, 0, host.ctypes.data, ctypes.c_void_p(dptr.value + offset), nbytes))
+        return host
+
+    def submit(self, body, n, out_dev, args_dev=None, arg_stride=0, index_start=0, task_base=0, want_sum=True, extra_flags=0, seed=0):
         a = self.abi
         spec = self.registry.spec(body)
         d = a.MapDesc()
         d.func_id = spec.func_id
-        d.flags = a.FBR_OUT_DEVICE | (a.FBR_WANT_SUM if want_sum else 0) | (a.FBR_ARGS_DEVICE if args_dev else 0)
+        d.flags = a.FBR_OUT_DEVICE | (a.FBR_WANT_SUM if want_sum else 0) | (a.FBR_ARGS_DEVICE if args_dev else 0) | extra_flags
         d.n_tasks, d.chunksize, d.arg_stride = n, 0, arg_stride
         d.args = args_dev
         d.index_start, d.index_step = index_start, 1
         d.out = out_dev
         d.task_index_base = task_base
+        d.shuffle_seed = seed
         seq = ctypes.c_uint64(0)
         a.check(self.lib.fbr_map_submit(self.h, ctypes.byref(d), ctypes.byref(seq)))
         return seq.value
@@ -274,68 +326,173 @@ def timed_steps(dist, steps, warmup, step_fn, drain_fn=None, clock_windows=None)
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: oracle port of the reference ZPool on this box's host cores
+# oracle helpers (checker only; never inside a timed region)
 # ------------------------------------------------------------------------------------------------
-def cpu_pool_arm(steps, warmup, n_tasks, processes):
+def _threads(n_jobs):
+    return max(1, min(n_jobs, (os.cpu_count() or 1) // 2, 32))
+
+
+def _parallel(jobs):
+    """Run callables on host threads (the C oracle releases the GIL) and return their results in order."""
+    out = [None] * len(jobs)
+    errs = []
+
+    def run(i):
+        try:
+            out[i] = jobs[i]()
+        except Exception as e:      # noqa: BLE001
+            errs.append(e)
+    nt = _threads(len(jobs))
+    idx = list(range(len(jobs)))
+    ths = [threading.Thread(target=lambda s=s: [run(i) for i in idx[s::nt]]) for s in range(nt)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    if errs:
+        raise errs[0]
+    return out
+
+
+def oracle_payload_equal(got_u32, t0):
+    """FULL comparison of mapped 4 KB records (rows of `got_u32`, task t0 + row) against the C oracle."""
+    import numpy as np
     from oracle import cref
-    from oracle.zpool_port import PortPool
-    cref.lib()   # build/load the C body before forking workers
-    pool = PortPool(processes)
-    pool.map(cref.pi_inside_det_c, range(1000))          # excludes lazy worker start-up
-    times, count = [], None
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        res = pool.map(cref.pi_inside_det_c, range(n_tasks))   # default chunksize 32, list in hand
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
-        count = sum(res)
+    n = got_u32.shape[0]
+    step = 8192
+    jobs = [(lambda a=a: bool(np.array_equal(got_u32[a:a + step], cref.payload_map(t0 + a, cref.payload_records(t0 + a, min(step, n - a))))))
+            for a in range(0, n, step)]
+    return all(_parallel(jobs))
+
+
+def oracle_pi_equal(got_u8, first):
+    """FULL comparison of ordered is_inside results (one byte each) against the C oracle."""
+    import numpy as np
+    from oracle import cref
+    n = got_u8.shape[0]
+    step = 1 << 24
+    jobs = [(lambda a=a: bool(np.array_equal(got_u8[a:a + step], cref.pi_inside_range(first + a, min(step, n - a))[0])))
+            for a in range(0, n, step)]
+    return all(_parallel(jobs))
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own pool (baseline/_ref/fiber), or its oracle port, in a child process
+# ------------------------------------------------------------------------------------------------
+def _cpu_child(spec):
+    """Runs in a fresh interpreter (`bench.py --cpu-child <json>`): the reference pool's workers re-import
+    __main__ (spawn), so the arm lives in its own process, bounded by the parent's timeout."""
+    kind, P, n, reps, warm = spec["kind"], spec["P"], spec["n"], spec["reps"], spec["warm"]
+    from oracle import cref
+    cref.lib()   # build/load the C body before the workers start
+    if kind == "reference":
+        import fiber
+        assert os.path.realpath(fiber.__file__).startswith(os.path.realpath(REF_DIR)), fiber.__file__
+        pool = fiber.Pool(P)
+        impl = "%s (fiber %s, socket_lib=%s)" % (type(pool).__name__, getattr(fiber, "__version__", "?"), __import__("fiber.socket").socket.socket_lib)
+    else:
+        from oracle.zpool_port import PortPool
+        pool = PortPool(P)
+        impl = "oracle/zpool_port.PortPool"
+    out = {"impl": impl}
+    if spec["work"] == "pi":
+        pool.map(cref.pi_inside_det_c, range(1000))          # excludes lazy worker start-up
+        times, count = [], None
+        for i in range(warm + reps):
+            t0 = time.perf_counter()
+            res = pool.map(cref.pi_inside_det_c, range(n))   # default chunksize 32, list in hand
+            dt = time.perf_counter() - t0
+            if i >= warm:
+                times.append(dt)
+            count = sum(res)
+        out.update({"times": times, "count": count})
+    else:   # parzen: exactly examples/parzen_estimation.py:22-40 (apply_async per width)
+        from oracle import bodies as B
+        xs, px, widths = B.parzen_example_inputs()
+        pool.map(cref.pi_inside_det_c, range(1000))
+        times = []
+        for i in range(reps):
+            t0 = time.perf_counter()
+            handles = [pool.apply_async(B.parzen_estimation, args=(xs, px, w)) for w in widths]
+            res = [h.get() for h in handles]
+            times.append(time.perf_counter() - t0)
+        res.sort()
+        out.update({"times": times, "n_tasks": len(widths), "first": list(res[0]), "last": list(res[-1])})
     pool.terminate()
     pool.join()
-    return times, count
+    print("CPU_CHILD_RESULT " + json.dumps(out), flush=True)
+
+
+def cpu_arm(work, P, n=CPU_SAMPLE_TASKS, reps=3, warm=1, timeout=420):
+    """-> (result dict, kind).  Tries the real reference first, then the port."""
+    kinds = ["reference", "port"] if os.path.isdir(os.path.join(REF_DIR, "fiber")) else ["port"]
+    last_err = None
+    for kind in kinds:
+        env = dict(os.environ)
+        paths = ([REF_DIR] if kind == "reference" else []) + [ROOT, env.get("PYTHONPATH", "")]
+        env["PYTHONPATH"] = os.pathsep.join(p for p in paths if p)
+        env.pop("RANK", None)
+        spec = {"kind": kind, "P": P, "n": n, "reps": reps, "warm": warm, "work": work}
+        try:
+            cp = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-child", json.dumps(spec)], env=env, cwd=ROOT,
+                                stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
+            for ln in cp.stdout.splitlines():
+                if ln.startswith("CPU_CHILD_RESULT "):
+                    return json.loads(ln[len("CPU_CHILD_RESULT "):]), kind
+            last_err = "%s arm printed no result (rc %d): %s" % (kind, cp.returncode, cp.stderr[-300:])
+        except subprocess.TimeoutExpired:
+            last_err = "%s arm timed out after %d s" % (kind, timeout)
+    raise RuntimeError(last_err)
 
 
 def run_reference(args, dist):
-    """--impl reference: the reference's own CPU implementation of the path.  /root/reference is a
-    pure-Python package that needs nnpy and cannot travel to the GPU box, so this arm is the oracle
-    port of ZPool (oracle/zpool_port.py; same messages, real processes, zmq PUSH/PULL) -- validated
-    against the real reference pool here."""
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores."""
     if dist.rank != 0:
         return
     cores = os.cpu_count() or 1
-    procs = max(1, cores)
-    times, count = cpu_pool_arm(args.steps, args.warmup, CPU_SAMPLE_TASKS, procs)
+    res, kind = cpu_arm("pi", cores, reps=max(1, args.steps), warm=max(0, min(args.warmup, 1)))
+    times = res["times"]
     total = sum(times)
     value = CPU_SAMPLE_TASKS * len(times) / total
+    extra = {}
+    try:        # examples/pi_estimation.py:15 uses Pool(processes=4): BASELINE.json configs[0]
+        r4, k4 = cpu_arm("pi", 4, reps=2, warm=0)
+        extra["pool4"] = {"value": CPU_SAMPLE_TASKS / min(r4["times"]), "unit": "tasks/s", "cores": 4, "kind": k4,
+                          "sample": "best of 2 Pool(4).map over %d tasks (BASELINE.json configs[0])" % CPU_SAMPLE_TASKS}
+    except Exception as e:      # noqa: BLE001
+        extra["pool4"] = {"unavailable": str(e)[:200]}
     line = {
         "impl": "reference", "metric": "pool_map_tasks_per_sec", "value": value, "unit": "tasks/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup,
         "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64->u8", "data": "synthetic",
         "config": {"workload": "pi_estimation Pool.map over 1e8 index tasks per GPU (BASELINE.json configs[1])",
-                   "step_sample": "one Pool(processes=%d).map of %d tasks, default chunksize 32" % (procs, CPU_SAMPLE_TASKS)},
-        "cpu_baseline": {"value": value, "unit": "tasks/s", "cores": procs, "kind": "port",
-                         "sample": "%d maps of %d pi_inside_det tasks (C body via ctypes), ZPool port, %d worker processes"
-                                   % (len(times), CPU_SAMPLE_TASKS, procs)},
+                   "step_sample": "one Pool(processes=%d).map of %d tasks, default chunksize 32 (a rate: the CPU pool's tasks/s "
+                                  "does not depend on the map length)" % (cores, CPU_SAMPLE_TASKS),
+                   "tasks_per_step": CPU_SAMPLE_TASKS},
+        "cpu_baseline": {"value": value, "unit": "tasks/s", "cores": cores, "kind": kind, "impl": res.get("impl"),
+                         "sample": "%d maps of %d pi_inside_det tasks (C body via ctypes), %d worker processes"
+                                   % (len(times), CPU_SAMPLE_TASKS, cores), **extra},
         "e2e": {"value": value, "unit": "tasks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "check": {"count": count},
+        "check": {"count": res["count"]},
     }
     print(json.dumps(line), flush=True)
 
 
-
-
+# ------------------------------------------------------------------------------------------------
+# multi-GPU sections
+# ------------------------------------------------------------------------------------------------
 def fused_peer_map(n_gpus, n_total, steps):
     """Root-resident 4 KB map over an in-process pool of `n_gpus` workers: inputs and ordered outputs
-    stay on GPU 0, workers reach them through NVLink peer loads/stores inside the dispatch / gather
-    kernels (no NCCL call on the data path)."""
+    stay on GPU 0; every worker's dispatch kernel bulk-loads its block from GPU 0 and bulk-stores its
+    results at their final index on GPU 0 over NVLink peer memory, in the same kernel -- the scatter,
+    the map and the gather are one launch per worker and the root's links run in both directions at once."""
     import numpy as np
     from fiber_b200 import _abi, registry
-    from oracle import cref
     lib = _abi.load()
     ids = (ctypes.c_int * n_gpus)(*range(n_gpus))
     h = ctypes.c_void_p()
-    _abi.check(lib.fbr_pool_create(n_gpus, ids, (n_total // n_gpus + 4096) * 4096, 0, ctypes.byref(h)))
+    _abi.check(lib.fbr_pool_create(n_gpus, ids, 64 << 20, 0, ctypes.byref(h)))
     try:
         din, dout = ctypes.c_void_p(), ctypes.c_void_p()
         _abi.check(lib.fbr_device_alloc(h, 0, n_total * 4096, ctypes.byref(din)))
@@ -354,29 +511,43 @@ def fused_peer_map(n_gpus, n_total, steps):
             _abi.check(lib.fbr_result_release(h, seq.value))
         for _ in range(3):
             step()
+        nvl = NvlinkCounters(0)
+        c0 = nvl.read()
         t0 = time.perf_counter()
         for _ in range(steps):
             step()
         dt = time.perf_counter() - t0
-        ok = True
-        for t in (0, n_total // 2, n_total - 8):
-            got = np.empty((8, 1024), dtype=np.uint32)
-            _abi.check(lib.fbr_memcpy_d2h(h, 0, got.ctypes.data, ctypes.c_void_p(dout.value + t * 4096), got.nbytes))
-            ok &= bool(np.array_equal(got, cref.payload_map(t, cref.payload_records(t, 8))))
+        c1 = nvl.read()
+        st = _abi.Stats()
+        _abi.check(lib.fbr_pool_stats(h, ctypes.byref(st)))
+        # FULL parity: every byte of the ordered output on GPU 0 against the C oracle
+        got = np.empty((n_total, 1024), dtype=np.uint32)
+        _abi.check(lib.fbr_memcpy_d2h(h, 0, got.ctypes.data, dout, got.nbytes))
+        ok = oracle_payload_equal(got, 0)
+        sha = hashlib.sha256(got.tobytes()).hexdigest()
+        del got
         lib.fbr_device_free(h, 0, din)
         lib.fbr_device_free(h, 0, dout)
-        link_bytes = 2 * n_total * 4096 * (n_gpus - 1) / n_gpus      # peer loads + peer stores through GPU 0's links
-        return {"value": n_total * steps / dt, "unit": "tasks/s", "ms_per_step": 1e3 * dt / steps,
-                "root_link_GBps_each_way": link_bytes / 2 / (dt / steps) / 1e9, "parity_spot_check": ok,
-                "note": "in-process Pool(%d): args/out on GPU 0, peer loads in dispatch + peer stores in gather over NVLink" % n_gpus}
+        link_bytes = n_total * 4096 * (n_gpus - 1) / n_gpus      # each way: peer loads out of / peer stores into GPU 0
+        out = {"value": n_total * steps / dt, "unit": "tasks/s", "ms_per_step": 1e3 * dt / steps,
+               "root_link_GBps_each_way": link_bytes / (dt / steps) / 1e9,
+               "nvlink_ref_GBps": 770.0, "frac_of_peer_copy_ref": link_bytes / (dt / steps) / 1e9 / 770.0,
+               "parity_full": ok, "checked_bytes": n_total * 4096, "sha256": sha,
+               "direct_waves": int(st.direct_waves), "gather_launches": int(st.gather_launches),
+               "note": "in-process Pool(%d): args/out on GPU 0; peer bulk loads + peer bulk stores inside ONE dispatch kernel per "
+                       "worker (direct placement), full duplex over NVLink" % n_gpus}
+        if c0 and c1:
+            out["nvml_gpu0_nvlink"] = {"tx_GBps": (c1[0] - c0[0]) / dt / 1e9, "rx_GBps": (c1[1] - c0[1]) / dt / 1e9,
+                                      "source": "NVML NVLINK_THROUGHPUT_DATA_TX/RX (all links) around the timed steps"}
+        return out
     finally:
         lib.fbr_pool_destroy(h)
-
 
 
 def inprocess_pool_e2e(n_gpus, steps):
     """The literal drop-in usage: ONE process, `fiber_b200.Pool(processes=N)` over all N GPUs,
     `pool.map(is_inside, range(N * 1e8))` -> one pinned ResultArray (each GPU D2Hs its block) + count."""
+    import numpy as np
     import fiber_b200
     from examples import workloads as W
     pool = fiber_b200.Pool(n_gpus)
@@ -386,7 +557,7 @@ def inprocess_pool_e2e(n_gpus, steps):
     def step():
         res = pool.map(W.is_inside, range(n))
         counts.append(res.sum())
-        del res
+        step.last = res
     for _ in range(3):
         step()
     k = max(3, min(steps, 10))
@@ -394,24 +565,30 @@ def inprocess_pool_e2e(n_gpus, steps):
     for _ in range(k):
         step()
     dt = time.perf_counter() - t0
+    # FULL parity of the last step's ordered results (bit-packed in the pinned segment) against the C oracle
+    got = np.unpackbits(step.last.packed, count=n, bitorder="little")
+    ok = oracle_pi_equal(got, 0) and counts[-1] == int(got.sum())
+    step.last = None
     pool.terminate()
     pool.join()
     return {"value": n * k / dt, "unit": "tasks/s", "ms_per_step": 1e3 * dt / k, "tasks_per_step": n, "count": counts[-1],
-            "api": "fiber_b200.Pool(%d).map(is_inside_det, range(%d)) in one process" % (n_gpus, n)}
+            "parity_full": ok, "checked_tasks": n,
+            "api": "fiber_b200.Pool(%d).map(is_inside_det, range(%d)) in one process -> pinned bit-packed ResultArray + count" % (n_gpus, n)}
 
 
 def run_multi_gpu(args, dist, dev):
     """BASELINE.json configs[3] and [4] on N GPUs (torch.distributed/NCCL is the exchange plumbing;
     the map itself runs through the C ABI on torch-allocated device buffers):
       * payload4k_sharded: 1e6 tasks TOTAL, contiguous block per rank (strong scaling):
-        (i) shard-resident, (ii) including NCCL scatter from rank 0 and gather to rank 0;
-      * ring_allreduce: 256 MiB fp32 all-reduce across the ring (experimental.Ring's collective)."""
+        (i) shard-resident, (ii) including NCCL scatter from rank 0 and gather to rank 0,
+        (iii) root-resident with scatter+gather fused into the dispatch kernel over peer memory;
+      * ring_allreduce: 256 MiB fp32 all-reduce across the ring (experimental.Ring's collective).
+    Every path's output is compared IN FULL with the C oracle outside the timed loops."""
     import numpy as np
     import torch
     import torch.distributed as td
     from fiber_b200 import _abi, shard
     from fiber_b200.experimental import allreduce_bench
-    from oracle import cref
 
     rank, world = dist.rank, dist.world
     n_total = PAYLOAD_TASKS
@@ -419,7 +596,7 @@ def run_multi_gpu(args, dist, dev):
     n_loc = hi - lo
     width = max(b - a for a, b in shard.blocks(n_total, world))
     cuda = torch.device("cuda", dev)
-    eng = RawEngine(dev, width * 4096 + (1 << 20))
+    eng = RawEngine(dev, 64 << 20)
     inp = torch.empty(width * 1024, dtype=torch.int32, device=cuda)
     out = torch.empty(width * 1024, dtype=torch.int32, device=cuda)
     _abi.check(eng.lib.fbr_payload_fill_device(eng.h, 0, ctypes.c_void_p(inp.data_ptr()), lo, n_loc))
@@ -444,15 +621,20 @@ def run_multi_gpu(args, dist, dev):
     eng.release_deferred()
     t_res = timed_steps(dist, args.steps, 0, submit_map, drain_maps)      # steps queue back to back
     eng.release_deferred()
+    # (i) full parity of this rank's shard-resident block
+    mine = out[: n_loc * 1024].cpu().numpy().view(np.uint32).reshape(n_loc, 1024)
+    ok_shard = dist.all_true(oracle_payload_equal(mine, lo))
+    del mine
 
     # (ii) scatter from rank 0 -> map -> gather to rank 0 (root-ingress bound over NVLink)
     full_in = full_out = None
     if rank == 0:
         full_in = torch.empty(world * width * 1024, dtype=torch.int32, device=cuda)
-        full_out = torch.empty(world * width * 1024, dtype=torch.int32, device=cuda)
+        full_out = torch.zeros(world * width * 1024, dtype=torch.int32, device=cuda)
         for r, (a, b) in enumerate(shard.blocks(n_total, world)):
             _abi.check(eng.lib.fbr_payload_fill_device(eng.h, 0, ctypes.c_void_p(full_in.data_ptr() + r * width * 4096), a, b - a))
         torch.cuda.synchronize()
+    out.zero_()
 
     def scattered_map():
         td.scatter(inp, list(full_in.chunk(world)) if rank == 0 else None, src=0)
@@ -466,18 +648,18 @@ def run_multi_gpu(args, dist, dev):
     eng.release_deferred()
     t_sc = timed_steps(dist, args.steps, 0, scattered_map)
     eng.release_deferred()
-    ok = True
-    if rank == 0:
+    ok_gathered = True
+    if rank == 0:       # full parity of the gathered output on rank 0, block by block
         for r, (a, b) in enumerate(shard.blocks(n_total, world)):
-            got = full_out[r * width * 1024: r * width * 1024 + 8 * 1024].cpu().numpy().view(np.uint32).reshape(8, 1024)
-            ok &= bool(np.array_equal(got, cref.payload_map(a, cref.payload_records(a, 8))))
+            blk = full_out[r * width * 1024: r * width * 1024 + (b - a) * 1024].cpu().numpy().view(np.uint32).reshape(b - a, 1024)
+            ok_gathered &= oracle_payload_equal(blk, a)
+            del blk
     eng.close()
     del inp, out, full_in, full_out
     torch.cuda.empty_cache()
 
-    # (iii) the same root-resident map with scatter and gather FUSED into the kernels: one in-process
-    # pool on rank 0 drives all N GPUs; arguments and ordered output live on GPU 0, every worker's
-    # dispatch kernel loads its block and its gather kernel stores its units over NVLink peer memory.
+    # (iii) the same root-resident map with scatter and gather FUSED into the dispatch kernel: one in-process
+    # pool on rank 0 drives all N GPUs; arguments and ordered output live on GPU 0.
     fused = inproc = None
     # the other ranks wait on the HOST (store key), not in an NCCL barrier: a spinning NCCL kernel on
     # their GPUs would compete with the peer traffic being measured
@@ -500,16 +682,100 @@ def run_multi_gpu(args, dist, dev):
         "payload4k_sharded": {
             "workload": "synthetic 4 KB-payload map, %d tasks TOTAL in contiguous blocks over %d GPUs (BASELINE.json configs[3])" % (n_total, world),
             "scaling": "strong",
-            "shard_resident": {"value": n_total * args.steps / t_res, "unit": "tasks/s", "ms_per_step": 1e3 * t_res / args.steps},
+            "shard_resident": {"value": n_total * args.steps / t_res, "unit": "tasks/s", "ms_per_step": 1e3 * t_res / args.steps,
+                               "parity_full": ok_shard, "checked_bytes": n_total * 4096},
             "scatter_map_gather_root0": {"value": n_total * args.steps / t_sc, "unit": "tasks/s", "ms_per_step": 1e3 * t_sc / args.steps,
+                                         "parity_full": ok_gathered, "checked_bytes": n_total * 4096,
                                          "note": "NCCL scatter from rank 0 + map + NCCL gather to rank 0; root link-bound"},
-            "fused_peer_memory_root0": fused,
-            "parity_spot_check": ok},
+            "fused_peer_memory_root0": fused},
         "inprocess_pool_e2e": inproc,
         "ring_allreduce": {"workload": "all-reduce SUM of 64 Mi fp32 (256 MiB) per rank, %d ranks (BASELINE.json configs[4])" % world,
                            "bit_exact": ar_ok, "algbw_GBps": algbw, "busbw_GBps": busbw, "ms": ar_ms,
                            "nvlink_ref": "measured refs: 725 GB/s all-reduce busbw @1 GiB, 770 GB/s peer copy (B200_PROFILING.md)"},
     }
+
+
+# ------------------------------------------------------------------------------------------------
+# parzen (BASELINE.json configs[2])
+# ------------------------------------------------------------------------------------------------
+def run_parzen(dev, traffic, with_cpu):
+    """102 window widths over the 10 000 x 2 sample set of examples/parzen_estimation.py:32-40 through
+    apply_async (as the example) and starmap(chunksize=1); fp32 body = the north-star's path."""
+    import numpy as np
+    import fiber_b200
+    from examples import workloads as W
+    from oracle import bodies as B, cref
+    xs, px, widths = B.parzen_example_inputs()
+    n = len(xs)
+    pool = fiber_b200.Pool(1, devices=[dev], timing=True)
+    items = [(xs, px, w) for w in widths]
+
+    def job_apply():
+        hs = [pool.apply_async(W.parzen_estimation_f32, args=(xs, px, w)) for w in widths]
+        return [h.get() for h in hs]
+
+    def job_star():
+        return pool.starmap(W.parzen_estimation_f32, items, 1)
+
+    out = {"workload": "parzen_estimation: %d samples x %d dims (seed 123), %d widths, fp32 window test (BASELINE.json configs[2])"
+                       % (n, xs.shape[1], len(widths))}
+    for name, fn, reps in (("apply_async_x102", job_apply, 5), ("starmap_chunksize1", job_star, 20)):
+        for _ in range(2):
+            res = fn()
+        pool.reset_stats()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            res = fn()
+        dt = (time.perf_counter() - t0) / reps
+        st = pool.stats()
+        out[name] = {"ms_per_job": 1e3 * dt, "tasks_per_s": len(widths) / dt, "kernel_launches_per_job": st["dispatch_launches"] / reps,
+                     "kernel_us_per_job": 1e3 * st["dispatch_ms"] / reps, "h2d_bytes_per_job": st["h2d_bytes"] // reps,
+                     "d2h_bytes_per_job": st["d2h_bytes"] // reps}
+    star = np.asarray(res)
+    # parity: k_n vs the CPU fp32 restatement (exact) and vs fp64 (boundary samples only), density rtol 1e-6
+    mism, ok = 0, True
+    for (h, dens), w in zip(star.tolist(), widths):
+        k_gpu = int(round(dens * h * n))
+        k32 = cref.parzen_count(xs, px, w, np.float32)
+        k64 = cref.parzen_count(xs, px, w, np.float64)
+        ok &= (h == w) and (k_gpu == k32) and abs(k_gpu - k64) <= B.parzen_boundary_count(xs, px, w)
+        if k_gpu == k64:
+            want = (k64 / n) / h
+            ok &= abs(dens - want) <= 1e-6 * abs(want)
+        else:
+            mism += 1
+    f64 = pool.starmap(W.parzen_estimation, items, 1)
+    ok64 = all((k == cref.parzen_count(xs, px, w, np.float64)) for (h, d), w, k in
+               zip(f64.tolist(), widths, [int(round(d * h * n)) for h, d in f64.tolist()]))
+    kern_us = out["starmap_chunksize1"]["kernel_us_per_job"]
+    l2_bytes = len(widths) * n * xs.shape[1] * 4
+    tr = traffic.get("dispatch_parzen_kernel@prof_parzen", {})
+    out.update({
+        "value": out["starmap_chunksize1"]["tasks_per_s"], "unit": "tasks/s",
+        "parity": {"k_n_equals_fp32_oracle_and_within_boundary_of_fp64": bool(ok), "fp32_vs_fp64_k_n_mismatches": mism,
+                   "tolerance": "k_gpu == k_cpu(fp32) exactly; may differ from fp64 only on samples with ||x|/h - 0.5| <= 2^-22*max(1,|x|/h); "
+                                "density rtol 1e-6 when k matches", "parzen_f64_k_n_bit_exact": bool(ok64)},
+        "roofline": {"kernel": "dispatch_parzen_kernel<float> (one CTA per width, samples re-read from L2)", "bound": "l2",
+                     "achieved": l2_bytes / (kern_us * 1e-6) / 1e9 if kern_us else None, "unit": "GB/s",
+                     "algorithmic_bytes_per_launch": l2_bytes, "avg_launch_us": kern_us,
+                     "lts_pct_of_peak": tr.get("lts_pct_of_peak"), "traffic": tr.get("dram_bytes_per_launch"),
+                     "note": "102 CTAs x 80 KB from L2 = 8.2 MB per launch: the launch is latency-bound (a few us), far below any "
+                             "bandwidth roof; lts_pct_of_peak comes from the committed ncu capture"},
+    })
+    pool.terminate()
+    pool.join()
+    if with_cpu:
+        try:
+            res_c, kind = cpu_arm("parzen", os.cpu_count() or 1, reps=2, timeout=300)
+            best = min(res_c["times"])
+            out["cpu_baseline"] = {"value": len(widths) / best, "unit": "tasks/s", "ms_per_job": 1e3 * best, "cores": os.cpu_count() or 1,
+                                   "kind": kind, "impl": res_c.get("impl"),
+                                   "sample": "best of 2: 102 apply_async calls of the reference's parzen_estimation (Python loops over "
+                                             "10 000 samples, float64) through Pool(processes=%d), as examples/parzen_estimation.py:22-28" % (os.cpu_count() or 1),
+                                   "first_result": res_c.get("first")}
+        except Exception as e:      # noqa: BLE001
+            out["cpu_baseline"] = {"unavailable": str(e)[:200]}
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -528,6 +794,7 @@ def run_ours(args, dist):
     peaks, peak_src = load_peaks()
     hbm_peak = float(peaks["hbm_gbs"])
     traffic, traffic_src = load_traffic()
+    traffic_commit = traffic.get("_meta", {}).get("commit")
 
     def traffic_of(key):
         return traffic.get(key, {}).get("dram_bytes_per_launch")
@@ -540,12 +807,15 @@ def run_ours(args, dist):
         clocks.start()
 
     # ---------------- value: device-resident, raw C ABI ------------------------------------------
-    eng = RawEngine(dev, 160 << 20)                       # one wave holds 1e8 one-byte results
+    eng = RawEngine(dev, 160 << 20)                       # (ring only used by the via-ring leg below)
     out_dev = eng.dalloc(PI_TASKS)
     pending = []
+    leg = {"flags": 0, "seed": 1}
 
     def pi_step():
-        pending.append(eng.submit("pi_inside_det", PI_TASKS, out_dev, index_start=my_first, task_base=my_first))
+        leg["seed"] += 1
+        pending.append(eng.submit("pi_inside_det", PI_TASKS, out_dev, index_start=my_first, task_base=my_first,
+                                  extra_flags=leg["flags"], seed=leg["seed"]))
 
     counts = []
 
@@ -567,21 +837,43 @@ def run_ours(args, dist):
     total_count = dist.sum_i64(my_count)
     value = world * PI_TASKS * args.steps / t_value
     launches_value = st["dispatch_launches"] + st["gather_launches"]
-    gather_ms = st["gather_ms"] / max(1, st["gather_launches"])
     dispatch_ms = st["dispatch_ms"] / max(1, st["dispatch_launches"])
-    gather_bytes = st["gather_bytes"] / max(1, st["gather_launches"])
-    roofline = {"kernel": "gather_rows_kernel (gather_ordered, 4 KB-row path)", "bound": "hbm",
+    # FULL parity of the device-resident ordered output of the last timed step (outside the timed loop)
+    value_parity = oracle_pi_equal(eng.d2h(out_dev, PI_TASKS), my_first)
+    value_parity = dist.all_true(value_parity)
+
+    # ---- the gather leg: same map, task records shuffled inside each wave -> records + ring + gather_ordered
+    leg["flags"] = _abi.FBR_SHUFFLE
+    for _ in range(3):
+        pi_step()
+    pi_drain()
+    eng.release_deferred()
+    eng.stats(reset=True)
+    t_ring = timed_steps(dist, args.steps, 0, pi_step, pi_drain, clocks.windows)
+    eng.release_deferred()
+    sr = eng.stats()
+    ring_parity = dist.all_true(oracle_pi_equal(eng.d2h(out_dev, PI_TASKS), my_first) and counts[-1] == my_count)
+    launches_ring = sr["dispatch_launches"] + sr["gather_launches"]
+    gather_ms = sr["gather_ms"] / max(1, sr["gather_launches"])
+    gather_bytes = sr["gather_bytes"] / max(1, sr["gather_launches"])
+    roofline = {"kernel": "gather_rows_kernel (gather_ordered, 4 KB-row path; placement by index under shuffled arrival)", "bound": "hbm",
                 "achieved": gather_bytes / (gather_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": gather_bytes / (gather_ms * 1e-3) / 1e9 / hbm_peak,
-                "traffic": traffic_of("gather_rows_kernel@prof_pi"), "traffic_source": traffic_src, "peak_source": peak_src,
+                "traffic": traffic_of("gather_rows_kernel@prof_pi"), "traffic_source": traffic_src, "traffic_capture_commit": traffic_commit,
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": gather_bytes, "avg_launch_ms": gather_ms,
-                "note": "2*R*N bytes (R=1 B) per launch; the ring was just written by the dispatch kernel so part of the reads can hit L2"}
+                "step_ms_via_ring": 1e3 * t_ring / args.steps, "tasks_per_s_via_ring": world * PI_TASKS * args.steps / t_ring,
+                "parity_full": ring_parity,
+                "note": "2*R*N bytes (R=1 B) per launch, 1e8 tasks; the ring (100 MB) was just written by the dispatch kernel, so part "
+                        "of it is still in the 126 MB L2 (`traffic` = DRAM bytes of the cold ncu capture); the DRAM-clean figures are "
+                        "payload4k.roofline_dispatch / roofline_gather (8.2 GB per launch).  The headline `value` step does not "
+                        "launch this kernel: a contiguous map is placed by the dispatch kernel itself"}
     # Philox4x32-10 + circle test: the bound is the SM's integer-multiply pipe (IMAD.WIDE.U32), not HBM
     # (1 B written per task).  Its peak is measured, not nominal: profiles/microbench/imad_peak.cu.
     wide_per_task = 18
     imad = load_imad_peak()
     wide_rate = wide_per_task * PI_TASKS / (dispatch_ms * 1e-3)
-    roofline_dispatch = {"kernel": "dispatch_thread_kernel<PiInsideDet, index args> (+ sum fold)", "bound": "alu (IMAD.WIDE.U32 pipe)",
+    roofline_dispatch = {"kernel": "dispatch_thread_kernel<PiInsideDet, index args> (+ sum fold, direct placement)", "bound": "alu (IMAD.WIDE.U32 pipe)",
                          "avg_launch_ms": dispatch_ms, "tasks_per_s": PI_TASKS / (dispatch_ms * 1e-3),
                          "hbm_gbs": PI_TASKS * 1 / (dispatch_ms * 1e-3) / 1e9,
                          "imad_wide_per_task": wide_per_task,
@@ -605,10 +897,11 @@ def run_ours(args, dist):
         out2 = eng.dalloc(PAYLOAD_TASKS * 4096)
         _abi.check(eng.lib.fbr_payload_fill_device(eng.h, 0, in_dev, t_base, PAYLOAD_TASKS))
         pend2 = []
+        pleg = {"flags": 0}
 
         def pl_step():
             pend2.append(eng.submit("payload_map_4k", PAYLOAD_TASKS, out2, args_dev=in_dev, arg_stride=4096,
-                                    task_base=t_base, want_sum=False))
+                                    task_base=t_base, want_sum=False, extra_flags=pleg["flags"]))
 
         def pl_drain():
             while pend2:
@@ -623,28 +916,42 @@ def run_ours(args, dist):
         sp = eng.stats()
         launches_payload = sp["dispatch_launches"] + sp["gather_launches"]
         d_ms = sp["dispatch_ms"] / max(1, sp["dispatch_launches"])
-        g_ms = sp["gather_ms"] / max(1, sp["gather_launches"])
         d_bytes = sp["dispatch_bytes"] / max(1, sp["dispatch_launches"])
-        g_bytes = sp["gather_bytes"] / max(1, sp["gather_launches"])
-        # parity spot check of the last step's output (first 64 tasks) against the oracle
-        host = np.empty((64, 1024), dtype=np.uint32)
-        _abi.check(eng.lib.fbr_memcpy_d2h(eng.h, 0, host.ctypes.data, out2, host.nbytes))
+        # FULL parity of the last step's output against the C oracle (4.1 GB, outside the timed loop)
+        got = eng.d2h(out2, PAYLOAD_TASKS * 4096).view(np.uint32).reshape(PAYLOAD_TASKS, 1024)
+        ok = dist.all_true(oracle_payload_equal(got, t_base))
+        del got
+        # via-ring leg: the same map through task records + ring + gather_bulk (TMA), for the gather's HBM roofline
+        pleg["flags"] = _abi.FBR_VIA_RING
+        for _ in range(2):
+            pl_step()
+        pl_drain()
+        eng.release_deferred()
+        eng.stats(reset=True)
+        k_ring = max(3, args.steps // 2)
+        t_plr = timed_steps(dist, k_ring, 0, pl_step, pl_drain, clocks.windows)
+        eng.release_deferred()
+        spr = eng.stats()
+        launches_payload += spr["dispatch_launches"] + spr["gather_launches"]
+        g_ms = spr["gather_ms"] / max(1, spr["gather_launches"])
+        g_bytes = spr["gather_bytes"] / max(1, spr["gather_launches"])
+        host = eng.d2h(out2, 64 * 4096).view(np.uint32).reshape(64, 1024)
         from oracle import cref
-        ok = bool(np.array_equal(host, cref.payload_map(t_base, cref.payload_records(t_base, 64))))
+        ok_ring = bool(np.array_equal(host, cref.payload_map(t_base, cref.payload_records(t_base, 64))))
         payload = {
             "workload": "synthetic 4 KB-payload map, %d tasks per GPU, inputs+outputs resident in HBM (4.1 GB each, >> L2)" % PAYLOAD_TASKS,
             "value": world * PAYLOAD_TASKS * args.steps / t_pl, "unit": "tasks/s", "ms_per_step": 1e3 * t_pl / args.steps,
-            "roofline_dispatch": {"kernel": "dispatch_payload_map_tma_kernel (TMA-staged, warp-specialised)", "bound": "hbm",
+            "roofline_dispatch": {"kernel": "dispatch_payload_map_tma_kernel (TMA-staged, warp-specialised, direct placement)", "bound": "hbm",
                                   "achieved": d_bytes / (d_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                   "frac": d_bytes / (d_ms * 1e-3) / 1e9 / hbm_peak, "avg_launch_ms": d_ms,
                                   "algorithmic_bytes_per_launch": d_bytes,
-                                  "traffic": traffic_of("dispatch_payload_map_tma_kernel@prof_payload")},
-            "roofline_gather": {"kernel": "gather_bulk_kernel (gather_ordered, TMA cp.async.bulk path)", "bound": "hbm",
+                                  "traffic": traffic_of("dispatch_payload_map_tma_kernel@prof_payload"), "traffic_capture_commit": traffic_commit},
+            "roofline_gather": {"kernel": "gather_bulk_kernel (gather_ordered, TMA cp.async.bulk path; FBR_VIA_RING leg)", "bound": "hbm",
                                 "achieved": g_bytes / (g_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                 "frac": g_bytes / (g_ms * 1e-3) / 1e9 / hbm_peak, "avg_launch_ms": g_ms,
-                                "algorithmic_bytes_per_launch": g_bytes,
-                                "traffic": traffic_of("gather_bulk_kernel@prof_payload")},
-            "parity_spot_check": ok,
+                                "algorithmic_bytes_per_launch": g_bytes, "step_ms_via_ring": 1e3 * t_plr / k_ring,
+                                "traffic": traffic_of("gather_bulk_kernel@prof_payload"), "traffic_capture_commit": traffic_commit},
+            "parity_full": ok, "checked_bytes": PAYLOAD_TASKS * 4096, "parity_spot_check_via_ring": ok_ring,
         }
         eng.dfree(in_dev)
         eng.dfree(out2)
@@ -664,7 +971,7 @@ def run_ours(args, dist):
         res = pool.map(W.is_inside, my_range)             # blocks until the pinned result segment is final
         c = res.sum()                                     # count folded on the device, read on the host
         e2e_counts.append(dist.sum_i64(c) if world > 1 else c)
-        del res
+        e2e_step.last = res
 
     for _ in range(max(args.warmup, 3)):
         e2e_step()
@@ -672,11 +979,16 @@ def run_ours(args, dist):
     t_e2e = timed_steps(dist, args.steps, 0, e2e_step, None, clocks.windows)
     se = pool.stats()
     e2e_value = world * PI_TASKS * args.steps / t_e2e
+    packed = e2e_step.last.packed
+    e2e_parity = dist.all_true(oracle_pi_equal(np.unpackbits(packed, count=PI_TASKS, bitorder="little"), my_first))
     e2e = {"value": e2e_value, "unit": "tasks/s", "ms_per_step": 1e3 * t_e2e / args.steps,
            "h2d_bytes_per_step": se["h2d_bytes"] // args.steps, "d2h_bytes_per_step": se["d2h_bytes"] // args.steps,
-           "api": "fiber_b200.Pool(1).map(is_inside_det, range(1e8)) -> pinned ResultArray + count",
+           "api": "fiber_b200.Pool(1).map(is_inside_det, range(1e8)) -> pinned ResultArray (bool results one bit each, the default layout) + count",
+           "packed_bytes": int(packed.nbytes), "parity_full": e2e_parity,
            "cpu_binding": ("%d GPU-local CPUs" % len(pool.bound_cpus)) if pool.bound_cpus else "none"}
     launches_e2e = se["dispatch_launches"] + se["gather_launches"]
+    e2e_step.last = None
+    del packed
 
     # e2e of the 4 KB payload map: records in pinned host memory -> H2D -> map -> D2H (PCIe-bound)
     if payload is not None:
@@ -712,7 +1024,7 @@ def run_ours(args, dist):
         del recs, got
         pl_e2e_step.last = None
     # secondary e2e: same call on Pool(results="device") -- ordered results stay in HBM, only the
-    # count (24-byte control block) crosses PCIe, as in `4.0 * pool.map(...).sum() / N`
+    # count (control block) crosses PCIe, as in `4.0 * pool.map(...).sum() / N`
     dpool = fiber_b200.Pool(1, devices=[dev], results="device")
     dev_counts = []
 
@@ -729,41 +1041,40 @@ def run_ours(args, dist):
     sd = dpool.stats()
     e2e["results_on_device"] = {"value": world * PI_TASKS * args.steps / t_e2e_dev, "unit": "tasks/s",
                                 "ms_per_step": 1e3 * t_e2e_dev / args.steps,
-                                "h2d_bytes_per_step": sd["h2d_bytes"] // args.steps, "d2h_bytes_per_step": sd["d2h_bytes"] // args.steps + 24,
+                                "h2d_bytes_per_step": sd["h2d_bytes"] // args.steps, "d2h_bytes_per_step": sd["d2h_bytes"] // args.steps + 32,
                                 "api": "fiber_b200.Pool(1, results='device').map(is_inside_det, range(1e8)).sum()",
                                 "count": dev_counts[-1],
                                 "note": "secondary figure: results are fetched lazily, only the folded count is read on the host"}
     launches_e2e += sd["dispatch_launches"] + sd["gather_launches"]
     dpool.terminate()
     dpool.join()
-    # secondary e2e: same call on Pool(results="bits") -- a bool travels as one bit (pi_inside_bits8):
-    # the ordered, bit-packed results of all 1e8 tasks reach the pinned host segment every step
-    bpool = fiber_b200.Pool(1, devices=[dev], results="bits")
-    bit_counts = []
+    # secondary e2e: same call on Pool(results="bytes") -- one BYTE per bool through the ordered output and PCIe
+    # (100 MB D2H per step: the PCIe floor of the byte layout)
+    bpool = fiber_b200.Pool(1, devices=[dev], results="bytes", bind_cpu=world > 1)
+    byte_counts = []
 
-    def e2e_bits_step():
+    def e2e_bytes_step():
         res = bpool.map(W.is_inside, my_range)
         c = res.sum()
-        bit_counts.append(dist.sum_i64(c) if world > 1 else c)
-        e2e_bits_step.last = res
+        byte_counts.append(dist.sum_i64(c) if world > 1 else c)
+        e2e_bytes_step.last = res
 
     for _ in range(3):
-        e2e_bits_step()
+        e2e_bytes_step()
     bpool.reset_stats()
-    t_e2e_bits = timed_steps(dist, args.steps, 0, e2e_bits_step, None, clocks.windows)
+    t_e2e_bytes = timed_steps(dist, args.steps, 0, e2e_bytes_step, None, clocks.windows)
     sb = bpool.stats()
-    packed = e2e_bits_step.last.packed
-    e2e["results_bit_packed"] = {"value": world * PI_TASKS * args.steps / t_e2e_bits, "unit": "tasks/s",
-                                 "ms_per_step": 1e3 * t_e2e_bits / args.steps,
-                                 "h2d_bytes_per_step": sb["h2d_bytes"] // args.steps, "d2h_bytes_per_step": sb["d2h_bytes"] // args.steps,
-                                 "api": "fiber_b200.Pool(1, results='bits').map(is_inside_det, range(1e8)) -> pinned bit-packed ResultArray + count",
-                                 "count": bit_counts[-1], "packed_bytes": int(packed.nbytes),
-                                 "parity_spot_check": bool(int(np.unpackbits(packed[:125000], bitorder="little").sum()) ==
-                                                           cref_count_first_1e6(my_first)),
-                                 "note": "secondary figure: same ordered bool results, 1 bit per task on the host (ResultArray unpacks on access)"}
+    arr = np.asarray(e2e_bytes_step.last).view(np.uint8)
+    e2e["results_byte_per_bool"] = {"value": world * PI_TASKS * args.steps / t_e2e_bytes, "unit": "tasks/s",
+                                    "ms_per_step": 1e3 * t_e2e_bytes / args.steps,
+                                    "h2d_bytes_per_step": sb["h2d_bytes"] // args.steps, "d2h_bytes_per_step": sb["d2h_bytes"] // args.steps,
+                                    "api": "fiber_b200.Pool(1, results='bytes').map(is_inside_det, range(1e8)) -> pinned uint8 ResultArray + count",
+                                    "count": byte_counts[-1],
+                                    "parity_spot_check": bool(int(arr[:10 ** 6].sum()) == cref_count_first_1e6(my_first)),
+                                    "note": "secondary figure: the opt-out layout, one byte per bool (PCIe-bound: 100 MB per step)"}
     launches_e2e += sb["dispatch_launches"] + sb["gather_launches"]
-    e2e_bits_step.last = None
-    del packed
+    e2e_bytes_step.last = None
+    del arr
     bpool.terminate()
     bpool.join()
 
@@ -776,18 +1087,25 @@ def run_ours(args, dist):
     pool.join()
     clk = clocks.stop() if rank == 0 else None
 
-    # ---------------- CPU baseline (rank 0, N=1) ------------------------------------------------------------
-    cpu = None
+    # ---------------- parzen (config 3) and the CPU baseline (rank 0, N=1) -------------------------------------
+    parzen = cpu = None
+    if rank == 0 and not args.skip_parzen:
+        parzen = run_parzen(dev, traffic, with_cpu=(world == 1 and not args.skip_cpu))
     if rank == 0 and world == 1 and not args.skip_cpu:
         cores = os.cpu_count() or 1
-        times, ccount = cpu_pool_arm(3, 1, CPU_SAMPLE_TASKS, cores)
-        best = min(times)
-        cpu = {"value": CPU_SAMPLE_TASKS / best, "unit": "tasks/s", "cores": cores, "kind": "port",
-               "sample": "best of 3 Pool(processes=%d).map over %d pi_inside_det tasks (C body), oracle ZPool port (zmq), "
+        res_c, kind = cpu_arm("pi", cores, reps=3, warm=1)
+        best = min(res_c["times"])
+        cpu = {"value": CPU_SAMPLE_TASKS / best, "unit": "tasks/s", "cores": cores, "kind": kind, "impl": res_c.get("impl"),
+               "sample": "best of 3 Pool(processes=%d).map over %d pi_inside_det tasks (C body via ctypes), default chunksize 32, "
                          "after a 1000-task warm-up map" % (cores, CPU_SAMPLE_TASKS),
-               "mean_tasks_per_s": CPU_SAMPLE_TASKS * len(times) / sum(times)}
-        from oracle import cref
-        assert ccount == cref.pi_inside_range(0, CPU_SAMPLE_TASKS, want_array=False)[1]
+               "mean_tasks_per_s": CPU_SAMPLE_TASKS * len(res_c["times"]) / sum(res_c["times"])}
+        assert res_c["count"] == cref_count_first_1e6(0)
+        try:
+            r4, k4 = cpu_arm("pi", 4, reps=2, warm=0)
+            cpu["pool4"] = {"value": CPU_SAMPLE_TASKS / min(r4["times"]), "unit": "tasks/s", "cores": 4, "kind": k4,
+                            "sample": "best of 2 Pool(4).map over %d tasks (examples/pi_estimation.py:15, BASELINE.json configs[0])" % CPU_SAMPLE_TASKS}
+        except Exception as e:      # noqa: BLE001
+            cpu["pool4"] = {"unavailable": str(e)[:200]}
 
     if rank == 0:
         line = {
@@ -796,12 +1114,16 @@ def run_ours(args, dist):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64->u8", "data": "synthetic",
             "config": {"workload": "pi_estimation Pool.map over 1e8 index tasks per GPU (BASELINE.json configs[1]), ordered uint8 results + int64 count",
                        "tasks_per_gpu": PI_TASKS, "chunksize": 32, "parallelism": "index blocks per rank, no data-path collective",
-                       "l2": "result ring (100 MB) + ordered output (100 MB) exceed the 126 MB L2; payload4k streams 8.2 GB per step"},
-            "e2e": e2e, "gpu_launches": int(launches_value + launches_payload + launches_e2e),
-            "gpu_launches_detail": {"pi_value_per_step": launches_value / args.steps, "payload_value_per_step": launches_payload / args.steps,
-                                    "e2e_paths_total": launches_e2e,
+                       "l2": "ordered output (100 MB per step) + the via-ring leg's result ring (100 MB) exceed the 126 MB L2; payload4k streams 8.2 GB per step",
+                       "cpu_arm_sample_tasks": CPU_SAMPLE_TASKS},
+            "e2e": e2e, "gpu_launches": int(launches_value + launches_ring + launches_payload + launches_e2e),
+            "gpu_launches_detail": {"pi_value_per_step": launches_value / args.steps, "pi_via_ring_per_step": launches_ring / args.steps,
+                                    "payload_total": launches_payload, "e2e_paths_total": launches_e2e,
                                     "note": "dispatch + gather launches of this repo's kernels inside the timed regions"},
-            "roofline": roofline, "roofline_dispatch": roofline_dispatch, "payload4k": payload,
+            "parity_full": {"value_leg": value_parity, "via_ring_leg": ring_parity, "e2e": e2e_parity,
+                            "payload4k": payload["parity_full"] if payload else None,
+                            "note": "every byte/bit of the last timed step's output compared with the C oracle, outside the timed loops"},
+            "roofline": roofline, "roofline_dispatch": roofline_dispatch, "payload4k": payload, "parzen": parzen,
             "multi_gpu": multi, "cpu_baseline": cpu, "clocks": clk,
             "check": {"pi_count_all_ranks": total_count, "pi_estimate": 4.0 * total_count / (world * PI_TASKS),
                       "e2e_count": e2e_counts[-1]},
@@ -818,7 +1140,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-payload", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-parzen", action="store_true")
+    ap.add_argument("--cpu-child", default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.cpu_child:
+        _cpu_child(json.loads(args.cpu_child))
+        return 0
     if args.impl == "reference":
         rank = int(os.environ.get("RANK", "0"))
         if rank != 0:

@@ -62,6 +62,26 @@ def parzen_estimation_f32(x_samples, point_x, h):
     _device_only("parzen_estimation_f32")
 
 
+@fiber_b200.device_initializer("parzen_f64")
+def set_parzen_samples(x_samples, point_x):
+    """Pool initializer (fiber/pool.py:858-859 runs it once per worker): the sample array every task shares
+    becomes the workers' broadcast block, uploaded once per device."""
+    _device_only("set_parzen_samples")
+
+
+@fiber_b200.device_body("parzen_f64")
+def parzen_at(h):
+    """parzen_estimation with the samples taken from the pool's initializer block."""
+    _device_only("parzen_at")
+
+
+@fiber_b200.device_body("trap_identity_i64")
+def trap_identity(i):
+    """Identity whose first attempt at an argument with low 20 bits 0xDEAD executes `trap` on the GPU: the
+    worker's CUDA context dies for real (the reference's worker process killed mid-chunk)."""
+    _device_only("trap_identity")
+
+
 @fiber_b200.device_body("payload_map_4k")
 def payload_map(t, rec):
     """BASELINE.json config 4: ``[(w * 2654435761 + t) & 0xFFFFFFFF for w in rec]``, rec = 1024 u32."""

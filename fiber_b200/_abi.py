@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libfiber_b200.so")
 
-FBR_ABI_VERSION = 1
+FBR_ABI_VERSION = 2
 
 # fbr_status
 FBR_OK, FBR_EINVAL, FBR_ECUDA, FBR_ENOMEM, FBR_ESTATE, FBR_ETIMEOUT, FBR_ETASK, FBR_ENODEV, FBR_ENOENT = \
@@ -24,14 +24,14 @@ FBR_POOL_TIMING, FBR_POOL_OVERLAP = 0x1, 0x2
 # map flags
 FBR_MAP, FBR_STARMAP, FBR_APPLY = 0x0, 0x1, 0x2
 FBR_ARGS_DEVICE, FBR_OUT_DEVICE, FBR_WANT_SUM, FBR_SHUFFLE, FBR_FULL_WINDOW, FBR_SHARED_HANDLE, FBR_RESILIENT, \
-    FBR_RESULTS_ON_DEVICE = 0x10, 0x20, 0x40, 0x80, 0x100, 0x200, 0x400, 0x800
+    FBR_RESULTS_ON_DEVICE, FBR_VIA_RING = 0x10, 0x20, 0x40, 0x80, 0x100, 0x200, 0x400, 0x800, 0x1000
 # fbr_task_error
 FBR_TASK_OK, FBR_TASK_OVERFLOW, FBR_TASK_BADARG, FBR_TASK_FAULT = range(4)
 
 # every symbol include/fiber_b200.h declares (tests check the .so exports each of them)
 SYMBOLS = [
     "fbr_abi_version", "fbr_last_error", "fbr_device_count",
-    "fbr_body_count", "fbr_body_info", "fbr_body_lookup",
+    "fbr_body_count", "fbr_body_info", "fbr_body_lookup", "fbr_register_body",
     "fbr_pool_create", "fbr_pool_close", "fbr_pool_terminate", "fbr_pool_join", "fbr_pool_destroy",
     "fbr_pool_n_workers", "fbr_pool_worker_device",
     "fbr_map_submit", "fbr_shared_put", "fbr_shared_drop", "fbr_plan_query",
@@ -43,7 +43,7 @@ SYMBOLS = [
     "fbr_lane_send", "fbr_lane_recv", "fbr_lane_poll", "fbr_queue_put", "fbr_queue_get", "fbr_queue_stats",
     "fbr_queue_destroy", "fbr_process_start", "fbr_process_poll", "fbr_process_join", "fbr_process_terminate",
     "fbr_process_handled", "fbr_process_destroy",
-    "fbr_express_last_error", "fbr_express_create", "fbr_express_submit", "fbr_express_wait", "fbr_express_stats",
+    "fbr_express_last_error", "fbr_express_create", "fbr_express_submit", "fbr_express_wait", "fbr_express_discard", "fbr_express_stats",
     "fbr_express_destroy",
 ]
 
@@ -66,7 +66,7 @@ class MapDesc(ctypes.Structure):
                 ("chunksize", ctypes.c_uint32), ("arg_stride", ctypes.c_uint32), ("args", ctypes.c_void_p),
                 ("index_start", ctypes.c_int64), ("index_step", ctypes.c_int64),
                 ("shared", ctypes.c_void_p), ("shared_bytes", ctypes.c_uint64), ("out", ctypes.c_void_p),
-                ("task_index_base", ctypes.c_uint64), ("shuffle_seed", ctypes.c_uint64)]
+                ("task_index_base", ctypes.c_uint64), ("shuffle_seed", ctypes.c_uint64), ("n_items", ctypes.c_uint64)]
 
 
 class Plan(ctypes.Structure):
@@ -77,7 +77,9 @@ class Plan(ctypes.Structure):
 class Result(ctypes.Structure):
     _fields_ = [("seq", ctypes.c_uint64), ("n_tasks", ctypes.c_uint64), ("result_bytes", ctypes.c_uint32),
                 ("result_kind", ctypes.c_uint32), ("data", ctypes.c_void_p), ("sum", ctypes.c_int64),
-                ("err_code", ctypes.c_uint32), ("n_waves", ctypes.c_uint32), ("err_task", ctypes.c_uint64)]
+                ("err_code", ctypes.c_uint32), ("n_waves", ctypes.c_uint32), ("err_task", ctypes.c_uint64),
+                ("sum_lo", ctypes.c_uint64), ("sum_hi", ctypes.c_int64), ("sum_overflow", ctypes.c_uint32),
+                ("pad", ctypes.c_uint32)]
 
 
 class Stats(ctypes.Structure):
@@ -87,7 +89,8 @@ class Stats(ctypes.Structure):
                 ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64),
                 ("dispatch_ms", ctypes.c_double), ("gather_ms", ctypes.c_double),
                 ("gather_bytes", ctypes.c_uint64), ("dispatch_bytes", ctypes.c_uint64),
-                ("units_redispatched", ctypes.c_uint64)]
+                ("units_redispatched", ctypes.c_uint64), ("records_copied", ctypes.c_uint64),
+                ("direct_waves", ctypes.c_uint64), ("workers_respawned", ctypes.c_uint64)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}
@@ -126,6 +129,7 @@ def load():
         "fbr_body_count": (i32, [P(i32)]),
         "fbr_body_info": (i32, [i32, P(BodyInfo)]),
         "fbr_body_lookup": (i32, [ctypes.c_char_p, P(i32)]),
+        "fbr_register_body": (i32, [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, P(i32)]),
         "fbr_pool_create": (i32, [i32, P(i32), u64, u32, P(vp)]),
         "fbr_pool_close": (i32, [vp]),
         "fbr_pool_terminate": (i32, [vp]),
@@ -172,6 +176,7 @@ def load():
         "fbr_express_create": (i32, [i32, i32, P(vp)]),
         "fbr_express_submit": (i32, [vp, i32, ctypes.c_char_p, u32, P(u64)]),
         "fbr_express_wait": (i32, [vp, u64, vp, P(u32), P(u32), i32]),
+        "fbr_express_discard": (i32, [vp, u64]),
         "fbr_express_stats": (i32, [vp, P(u64), P(u64), P(i32)]),
         "fbr_express_destroy": (i32, [vp]),
     }

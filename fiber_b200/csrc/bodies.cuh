@@ -25,8 +25,9 @@ enum FuncId : int32_t {
     F_PAYLOAD_CHECKSUM_4K = 8,  // 4 KB record -> u32
     F_SLEEP_F64 = 9,         // tests/test_pool.py:56-57   sleep_worker(duration) -> None
     F_FAULT_IDENTITY_I64 = 10,  // identity with injected faults (resilient pool tests)
-    F_PI_INSIDE_BITS8 = 11,  // pi_inside_det over 8 consecutive range() indices -> one byte, bit k = index 8g+k
-    F_COUNT = 12
+    F_PI_INSIDE_BITS8 = 11,  // pi_inside_det over 8 consecutive items (range() indices or int64 arguments) -> one byte, bit k = item 8g+k
+    F_TRAP_IDENTITY_I64 = 12,  // identity that executes `trap` on chosen arguments: kills the worker's CUDA context for real
+    F_COUNT = 13             // compiled-in bodies; bodies registered at run time (fbr_register_body) get ids from here up
 };
 
 enum TaskError : uint32_t { TASK_OK = 0, TASK_OVERFLOW = 1, TASK_BADARG = 2, TASK_FAULT = 3 };
@@ -249,6 +250,19 @@ struct FaultIdentityI64 {
     __device__ static __forceinline__ Res run(const Arg& a, uint64_t gidx, const ErrSink& es, uint32_t attempt) {
         const uint64_t h = splitmix64((gidx << 8) ^ (uint64_t)attempt ^ 0xFA17ull);
         if ((h % 100ull) < 5ull) es.report(TASK_FAULT, gidx);
+        return a;
+    }
+};
+// Identity whose first attempt at an argument with low 20 bits 0xDEAD executes `trap`: the kernel dies, the
+// device's context takes a sticky error and every later call on it fails -- a worker process killed for real
+// (the reference's dead worker: fiber/pool.py:1623-1656 notices it and re-queues its chunks elsewhere).
+struct TrapIdentityI64 {
+    using Arg = int64_t; using Res = int64_t;
+    static constexpr bool kIndexArg = true;
+    static constexpr bool kVecIndex = false;
+    static constexpr bool kCanFault = false;
+    __device__ static __forceinline__ Res run(const Arg& a, uint64_t, const ErrSink&, uint32_t attempt) {
+        if (attempt == 0u && ((uint64_t)a & 0xFFFFFull) == 0xDEADull) asm volatile("trap;");
         return a;
     }
 };

@@ -11,6 +11,7 @@
 // wave w's kernels.  No host thread is needed: ordering is carried by stream events, completion
 // by events the caller waits on (fbr_result_wait / fbr_result_poll).
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -21,6 +22,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <deque>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -55,12 +57,17 @@ static int fail(int code, const char* fmt, ...) {
     } while (0)
 
 // ------------------------------------------------------------------------------------------------
-// body table
+// body table: the compiled-in bodies plus bodies registered at run time from separately compiled
+// modules (fbr_register_body).  The reference ships ANY callable to its workers (fiber/pool.py:961,
+// executed at :806,809,820); here a callable's device body may live outside this library.
 // ------------------------------------------------------------------------------------------------
-typedef void (*launch_fn)(const WaveParams&, int grid, cudaStream_t);
+typedef void (*launch_fn)(const void* wave_params, int grid, void* stream);
+typedef int (*occupancy_fn)(int index_mode);
 
 template <class B>
-static void launch_thread(const WaveParams& wp, int grid, cudaStream_t s) {
+static void launch_thread(const void* wpv, int grid, void* sv) {
+    const WaveParams& wp = *(const WaveParams*)wpv;
+    cudaStream_t s = (cudaStream_t)sv;
     if constexpr (B::kIndexArg) {
         if (wp.arg_stride == 0) {
             dispatch_thread_kernel<B, true><<<grid, kThreads, 0, s>>>(wp);
@@ -69,7 +76,21 @@ static void launch_thread(const WaveParams& wp, int grid, cudaStream_t s) {
     }
     dispatch_thread_kernel<B, false><<<grid, kThreads, 0, s>>>(wp);
 }
-static void launch_payload_map(const WaveParams& wp, int grid, cudaStream_t s) {
+static int occ_of(const void* kernel) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, 0) != cudaSuccess) { cudaGetLastError(); return 1; }
+    return occ > 0 ? occ : 1;
+}
+template <class B>
+static int occ_thread(int index_mode) {
+    if constexpr (B::kIndexArg) {
+        if (index_mode) return occ_of((const void*)dispatch_thread_kernel<B, true>);
+    }
+    return occ_of((const void*)dispatch_thread_kernel<B, false>);
+}
+static void launch_payload_map(const void* wpv, int grid, void* sv) {
+    const WaveParams& wp = *(const WaveParams*)wpv;
+    cudaStream_t s = (cudaStream_t)sv;
     // contiguous records: TMA-staged, warp-specialised kernel (2 CTAs of 5 warps per SM); strided
     // records (arg_stride > 4096) keep the register-streaming kernel
     static const bool use_tma = !(getenv("FBR_DISPATCH_TMA") && atoi(getenv("FBR_DISPATCH_TMA")) == 0);
@@ -85,55 +106,84 @@ static void launch_payload_map(const WaveParams& wp, int grid, cudaStream_t s) {
     }
     dispatch_payload_map_kernel<<<grid, kThreads, 0, s>>>(wp);
 }
-static void launch_payload_checksum(const WaveParams& wp, int grid, cudaStream_t s) {
-    dispatch_payload_checksum_kernel<<<grid, kThreads, 0, s>>>(wp);
+static int occ_payload_map(int) {
+    cudaFuncSetAttribute(dispatch_payload_map_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_map::kSmemBytes);
+    cudaFuncAttributes at;
+    cudaFuncGetAttributes(&at, (const void*)dispatch_payload_map_tma_kernel);   // force-load
+    return occ_of((const void*)dispatch_payload_map_kernel);
 }
-static void launch_pi_bits(const WaveParams& wp, int grid, cudaStream_t s) {
-    dispatch_pi_bits_kernel<<<grid, kThreads, 0, s>>>(wp);
+static void launch_payload_checksum(const void* wpv, int grid, void* sv) {
+    dispatch_payload_checksum_kernel<<<grid, kThreads, 0, (cudaStream_t)sv>>>(*(const WaveParams*)wpv);
+}
+static int occ_payload_checksum(int) { return occ_of((const void*)dispatch_payload_checksum_kernel); }
+// bit-packed twin of a bool body: range() indices through the body's own 16-index vector routine,
+// explicit argument items through the generic ballot kernel
+static void launch_pi_bits(const void* wpv, int grid, void* sv) {
+    const WaveParams& wp = *(const WaveParams*)wpv;
+    if (wp.arg_stride == 0) dispatch_pi_bits_kernel<<<grid, kThreads, 0, (cudaStream_t)sv>>>(wp);
+    else dispatch_bits_items_kernel<PiInsideDet><<<grid, kThreads, 0, (cudaStream_t)sv>>>(wp);
+}
+static int occ_pi_bits(int index_mode) {
+    return index_mode ? occ_of((const void*)dispatch_pi_bits_kernel) : occ_of((const void*)dispatch_bits_items_kernel<PiInsideDet>);
 }
 template <typename T>
-static void launch_parzen(const WaveParams& wp, int grid, cudaStream_t s) {
-    dispatch_parzen_kernel<T><<<grid, kThreads, 0, s>>>(wp);
+static void launch_parzen(const void* wpv, int grid, void* sv) {
+    dispatch_parzen_kernel<T><<<grid, kThreads, 0, (cudaStream_t)sv>>>(*(const WaveParams*)wpv);
 }
+template <typename T>
+static int occ_parzen(int) { return occ_of((const void*)dispatch_parzen_kernel<T>); }
 
 struct BodyEntry {
-    const char* name;
-    uint32_t arg_bytes, result_bytes, result_kind, flags, unit_tasks;
-    launch_fn launch;
-    const void* kernel;
-    int max_ctas_per_sm;   // 0 = as many as fit; streaming read+write bodies run best with few, fat streams
-    const void* kernel_index = nullptr;   // the range()-argument instantiation (arg_stride == 0), if the body has one
+    std::string name;
+    uint32_t arg_bytes = 0, result_bytes = 0, result_kind = 0, flags = 0, unit_tasks = 0;
+    launch_fn launch = nullptr;
+    occupancy_fn occupancy = nullptr;
+    int max_ctas_per_sm = 0;   // 0 = as many as fit; streaming read+write bodies run best with few, fat streams
+    void* module = nullptr;    // dlopen handle of a registered body (never closed: kernels may be in flight)
 };
 
-static const BodyEntry kBodies[F_COUNT] = {
-    {"square_i64", 8, 8, FBR_RES_I64, FBR_BODY_INDEX_ARG | FBR_BODY_SUMMABLE, 4096, launch_thread<SquareI64>,
-     (const void*)dispatch_thread_kernel<SquareI64, false>, 0,
-     (const void*)dispatch_thread_kernel<SquareI64, true>},
-    {"mul2_i64", 16, 8, FBR_RES_I64, FBR_BODY_SUMMABLE, 4096, launch_thread<Mul2I64>,
-     (const void*)dispatch_thread_kernel<Mul2I64, false>, 0},
-    {"square_scale_i64", 16, 8, FBR_RES_I64, FBR_BODY_SUMMABLE, 4096, launch_thread<SquareScaleI64>,
-     (const void*)dispatch_thread_kernel<SquareScaleI64, false>, 0},
-    {"identity_i64", 8, 8, FBR_RES_I64, FBR_BODY_INDEX_ARG | FBR_BODY_SUMMABLE, 4096, launch_thread<IdentityI64>,
-     (const void*)dispatch_thread_kernel<IdentityI64, false>, 0,
-     (const void*)dispatch_thread_kernel<IdentityI64, true>},
-    {"pi_inside_det", 8, 1, FBR_RES_BOOL, FBR_BODY_INDEX_ARG | FBR_BODY_SUMMABLE, 4096, launch_thread<PiInsideDet>,
-     (const void*)dispatch_thread_kernel<PiInsideDet, false>, 0,
-     (const void*)dispatch_thread_kernel<PiInsideDet, true>},
-    {"parzen_f32", 8, 16, FBR_RES_F64X2, FBR_BODY_NEEDS_SHARED, 1, launch_parzen<float>,
-     (const void*)dispatch_parzen_kernel<float>, 0},
-    {"parzen_f64", 8, 16, FBR_RES_F64X2, FBR_BODY_NEEDS_SHARED, 1, launch_parzen<double>,
-     (const void*)dispatch_parzen_kernel<double>, 0},
-    {"payload_map_4k", 4096, 4096, FBR_RES_BYTES, 0, 32, launch_payload_map, (const void*)dispatch_payload_map_kernel,
-     3 /* measured: 3 CTAs/SM = 6641 GB/s, 8 CTAs/SM = 6296 GB/s on the 8.2 GB wave */},
-    {"payload_checksum_4k", 4096, 4, FBR_RES_U32, FBR_BODY_SUMMABLE, 256, launch_payload_checksum,
-     (const void*)dispatch_payload_checksum_kernel, 0},
-    {"sleep_f64", 8, 1, FBR_RES_NONE, 0, 1, launch_thread<SleepF64>, (const void*)dispatch_thread_kernel<SleepF64, false>, 0},
-    {"fault_identity_i64", 8, 8, FBR_RES_I64, FBR_BODY_INDEX_ARG | FBR_BODY_SUMMABLE, 2, launch_thread<FaultIdentityI64>,
-     (const void*)dispatch_thread_kernel<FaultIdentityI64, false>, 0,
-     (const void*)dispatch_thread_kernel<FaultIdentityI64, true>},
-    {"pi_inside_bits8", 8, 1, FBR_RES_BITS8, FBR_BODY_INDEX_ARG | FBR_BODY_INDEX_ONLY | FBR_BODY_SUMMABLE, 512, launch_pi_bits,
-     (const void*)dispatch_pi_bits_kernel, 0},
-};
+static std::mutex g_body_mu;
+static std::deque<BodyEntry> g_bodies;   // append-only: references stay valid, func_id = position
+
+static void builtin_bodies_once() {
+    // caller holds g_body_mu
+    if (!g_bodies.empty()) return;
+    auto add = [](const char* name, uint32_t ab, uint32_t rb, uint32_t kind, uint32_t flags, uint32_t unit, launch_fn l,
+                  occupancy_fn o, int max_ctas) {
+        BodyEntry b;
+        b.name = name; b.arg_bytes = ab; b.result_bytes = rb; b.result_kind = kind; b.flags = flags; b.unit_tasks = unit;
+        b.launch = l; b.occupancy = o; b.max_ctas_per_sm = max_ctas;
+        g_bodies.push_back(b);
+    };
+    // order == enum FuncId (bodies.cuh)
+    add("square_i64", 8, 8, FBR_RES_I64, FBR_BODY_INDEX_ARG | FBR_BODY_SUMMABLE, 4096, launch_thread<SquareI64>, occ_thread<SquareI64>, 0);
+    add("mul2_i64", 16, 8, FBR_RES_I64, FBR_BODY_SUMMABLE, 4096, launch_thread<Mul2I64>, occ_thread<Mul2I64>, 0);
+    add("square_scale_i64", 16, 8, FBR_RES_I64, FBR_BODY_SUMMABLE, 4096, launch_thread<SquareScaleI64>, occ_thread<SquareScaleI64>, 0);
+    add("identity_i64", 8, 8, FBR_RES_I64, FBR_BODY_INDEX_ARG | FBR_BODY_SUMMABLE, 4096, launch_thread<IdentityI64>, occ_thread<IdentityI64>, 0);
+    add("pi_inside_det", 8, 1, FBR_RES_BOOL, FBR_BODY_INDEX_ARG | FBR_BODY_SUMMABLE, 4096, launch_thread<PiInsideDet>, occ_thread<PiInsideDet>, 0);
+    add("parzen_f32", 8, 16, FBR_RES_F64X2, FBR_BODY_NEEDS_SHARED, 1, launch_parzen<float>, occ_parzen<float>, 0);
+    add("parzen_f64", 8, 16, FBR_RES_F64X2, FBR_BODY_NEEDS_SHARED, 1, launch_parzen<double>, occ_parzen<double>, 0);
+    add("payload_map_4k", 4096, 4096, FBR_RES_BYTES, 0, 32, launch_payload_map, occ_payload_map,
+        3 /* measured: 3 CTAs/SM = 6641 GB/s, 8 CTAs/SM = 6296 GB/s on the 8.2 GB wave */);
+    add("payload_checksum_4k", 4096, 4, FBR_RES_U32, FBR_BODY_SUMMABLE, 256, launch_payload_checksum, occ_payload_checksum, 0);
+    add("sleep_f64", 8, 1, FBR_RES_NONE, 0, 1, launch_thread<SleepF64>, occ_thread<SleepF64>, 0);
+    add("fault_identity_i64", 8, 8, FBR_RES_I64, FBR_BODY_INDEX_ARG | FBR_BODY_SUMMABLE, 2, launch_thread<FaultIdentityI64>, occ_thread<FaultIdentityI64>, 0);
+    // a byte-task = 8 items: 8 range() indices (arg_stride 0) or 8 int64 argument items (arg_stride 64)
+    add("pi_inside_bits8", 64, 1, FBR_RES_BITS8, FBR_BODY_INDEX_ARG | FBR_BODY_SUMMABLE, 512, launch_pi_bits, occ_pi_bits, 0);
+    add("trap_identity_i64", 8, 8, FBR_RES_I64, FBR_BODY_INDEX_ARG | FBR_BODY_SUMMABLE, 4096, launch_thread<TrapIdentityI64>, occ_thread<TrapIdentityI64>, 0);
+}
+static int body_count() {
+    std::lock_guard<std::mutex> g(g_body_mu);
+    builtin_bodies_once();
+    return (int)g_bodies.size();
+}
+// nullptr if func_id is out of range
+static const BodyEntry* body_of(int func_id) {
+    std::lock_guard<std::mutex> g(g_body_mu);
+    builtin_bodies_once();
+    if (func_id < 0 || func_id >= (int)g_bodies.size()) return nullptr;
+    return &g_bodies[func_id];
+}
 
 // ------------------------------------------------------------------------------------------------
 // pool structures
@@ -145,12 +195,13 @@ constexpr int kCtrlSlots = 65536;      // maps in flight (submitted, not yet rel
 constexpr int kTickets = 64;
 
 struct SeqCtrl {              // per (seq, worker) control block, device + pinned mirror
-    long long sum;
+    long long sum;            // 8-byte results: sum of the low 32-bit halves; other kinds: the sum itself
     unsigned long long err;   // (task_index << 8 | code), ~0 = none
     uint32_t lost_count;
     uint32_t pad;
+    long long sum_hi;         // 8-byte results: sum of the high halves (exact total = sum_hi * 2^32 + sum)
 };
-static_assert(sizeof(SeqCtrl) == 24, "");
+static_assert(sizeof(SeqCtrl) == 32, "");
 
 struct Worker {
     int device = -1;
@@ -173,11 +224,18 @@ struct Worker {
     cudaEvent_t ev_disp[kRecWindows];      // wave's dispatch kernel finished (its gather may start)
     cudaEvent_t ev_out[2];                 // out half's D2H finished
     uint64_t wave_no = 0;
-    int occ[F_COUNT];
-    int occ_index[F_COUNT];            // occupancy of the range()-argument instantiations
+    std::vector<int> occ, occ_index;   // per func_id: resident CTAs/SM of the explicit-argument / range() instantiation (0 = not asked yet)
     int occ_gather = 1, occ_fill = 1, occ_gather_rows = 1;
     std::vector<int> ctrl_free;        // free-list of control-block slots
 };
+
+// resident CTAs per SM of body `func_id` on this worker's device (current device must be w.device)
+static int worker_occ(Worker& w, int func_id, const BodyEntry& body, bool index_mode) {
+    std::vector<int>& v = index_mode ? w.occ_index : w.occ;
+    if ((int)v.size() <= func_id) v.resize(func_id + 1, 0);
+    if (v[func_id] == 0) v[func_id] = std::max(1, body.occupancy(index_mode ? 1 : 0));
+    return v[func_id];
+}
 
 struct TimedPair { cudaEvent_t a, b; };
 
@@ -185,10 +243,13 @@ struct PartCtx {                          // constants of one worker's block of 
     uint32_t unit = 0, slot_stride = 0, R = 0, sum_kind = 0;
     bool args_dev = false, out_dev = false, full_window = false, host_args = false, resilient = false, keep_on_device = false;
     bool overlap = false;                 // gather(w) on s_gath concurrently with dispatch(w+1); ring used in halves
+    bool direct = false;                  // contiguous, unshuffled, non-resilient block: the dispatch kernel stores every
+                                          // unit at its final index (no ring, no task records, no gather launch)
     const uint8_t* d_shared = nullptr;
     uint8_t* window_base = nullptr;       // device output of a FULL_WINDOW part
     const uint8_t* args_full = nullptr;   // device-resident arguments of the whole map (args_dev / resilient)
     uint64_t wave_tasks_cap = 0;
+    uint64_t args_limit_bytes = 0;        // host arguments end here (n_items records); 0 = n_tasks * arg_stride
 };
 
 struct SeqPart {
@@ -216,7 +277,10 @@ struct SeqState {
     void* out = nullptr;
     bool own_out = false;
     bool finished = false;
-    int64_t sum = 0;
+    int64_t sum = 0;              // total wrapped to int64 ...
+    uint64_t sum_lo = 0;          // ... and its exact form: sum_hi * 2^32 + sum_lo
+    int64_t sum_hi = 0;
+    bool sum_overflow = false;    // the exact total does not fit int64
     uint32_t err_code = 0;
     uint64_t err_task = 0;
     uint32_t n_waves = 0;
@@ -382,7 +446,7 @@ static int worker_init(fbr_pool* p, Worker& w, int device) {
     CK(cudaMemsetAsync(w.d_tickets, 0, sizeof(uint32_t) * kTickets * 2, w.s_comp));
     CK(cudaMalloc((void**)&w.d_ctrl, sizeof(SeqCtrl) * kCtrlSlots));
     CK(cudaHostAlloc((void**)&w.h_ctrl, sizeof(SeqCtrl) * (kCtrlSlots + 1), cudaHostAllocPortable));
-    w.h_ctrl[kCtrlSlots] = SeqCtrl{0, ~0ull, 0u, 0u};
+    w.h_ctrl[kCtrlSlots] = SeqCtrl{0, ~0ull, 0u, 0u, 0};
     w.ctrl_free.resize(kCtrlSlots);
     for (int i = 0; i < kCtrlSlots; ++i) w.ctrl_free[i] = kCtrlSlots - 1 - i;
     for (int i = 0; i < kRecWindows; ++i) {
@@ -391,22 +455,18 @@ static int worker_init(fbr_pool* p, Worker& w, int device) {
         CK(cudaEventCreateWithFlags(&w.ev_disp[i], cudaEventDisableTiming));
     }
     for (int i = 0; i < 2; ++i) CK(cudaEventCreateWithFlags(&w.ev_out[i], cudaEventDisableTiming));
-    for (int f = 0; f < F_COUNT; ++f) {
-        int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kBodies[f].kernel, kThreads, 0));
-        w.occ[f] = occ > 0 ? occ : 1;
-        w.occ_index[f] = w.occ[f];
-        if (kBodies[f].kernel_index) {
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kBodies[f].kernel_index, kThreads, 0));
-            w.occ_index[f] = occ > 0 ? occ : 1;
-        }
+    // occupancy of every body known now (also force-loads their kernels: a lazy module load would
+    // synchronise with resident device processes, queues.cu); bodies registered later are asked on first use
+    for (int f = 0, n = body_count(); f < n; ++f) {
+        const BodyEntry& b = *body_of(f);
+        worker_occ(w, f, b, false);
+        if (b.flags & FBR_BODY_INDEX_ARG) worker_occ(w, f, b, true);
     }
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w.occ_gather, (const void*)gather_ordered_kernel, kThreads, 0));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w.occ_fill, (const void*)payload_fill_kernel, kThreads, 0));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w.occ_gather_rows, (const void*)gather_rows_kernel, kThreads, 0));
     if (w.occ_gather_rows < 1) w.occ_gather_rows = 1;
     CK(cudaFuncSetAttribute(gather_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bulk::kStages * bulk::kChunk)));
-    CK(cudaFuncSetAttribute(dispatch_payload_map_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_map::kSmemBytes));
     if (w.occ_gather < 1) w.occ_gather = 1;
     if (w.occ_fill < 1) w.occ_fill = 1;
     // no cudaDeviceSynchronize here: it would wait for resident device processes (queues.cu)
@@ -479,11 +539,13 @@ static void shuffle_records(TaskRecord* r, uint32_t n, uint64_t seed) {
 // ------------------------------------------------------------------------------------------------
 // wave pipeline for one worker's block of one map
 // ------------------------------------------------------------------------------------------------
-// One wave: `n_units` task records already written into the pinned window `hrec` -> copy-in,
-// dispatch, gather, (streaming parts) copy-out.  `wave_first`/`wt` describe the contiguous task
-// window of a regular wave; a re-dispatch wave (arbitrary lost units) passes contiguous=false.
+// One wave: `n_units` claim units -> copy-in, dispatch, gather, (streaming parts) copy-out.
+// `wave_first`/`wt` describe the contiguous task window of a regular wave; a re-dispatch wave
+// (arbitrary lost units) passes contiguous=false.  `have_records`: the caller wrote the wave's task
+// records into the pinned window (shuffled, resilient or re-dispatch waves); otherwise the records
+// are an arithmetic progression the kernels compute themselves.
 static int run_wave(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry& body, uint32_t n_units,
-                    uint64_t wave_first, uint64_t wt, bool contiguous, uint64_t wno) {
+                    uint64_t wave_first, uint64_t wt, bool contiguous, bool have_records, uint64_t wno) {
     Worker& w = p->workers[part.worker];
     const PartCtx& cx = part.cx;
     const fbr_map_desc_t& d = st.desc;
@@ -491,19 +553,28 @@ static int run_wave(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry& b
     const int rw = (int)(wno % kRecWindows);
     const int half = (int)(wno & 1);
     const int slot = part.ctrl_slot;
+    const bool direct = cx.direct && contiguous && !have_records;
     TaskRecord* hrec = w.h_records + (size_t)rw * kRecCapacity;
     TaskRecord* drec = w.d_records + (size_t)rw * kRecCapacity;
 
     // copy-in stream: wait until the device window / arg half were consumed, then H2D
     CK(cudaStreamWaitEvent(w.s_in, w.ev_comp[rw], 0));  // wave wno-4 kernels done (device window free)
     if (wno >= 2) CK(cudaStreamWaitEvent(w.s_in, w.ev_comp[(wno - 2) % kRecWindows], 0));  // arg half free
-    CK(cudaMemcpyAsync(drec, hrec, sizeof(TaskRecord) * n_units, cudaMemcpyHostToDevice, w.s_in));
-    p->stats.h2d_bytes += sizeof(TaskRecord) * n_units;
+    if (have_records) {
+        CK(cudaMemcpyAsync(drec, hrec, sizeof(TaskRecord) * n_units, cudaMemcpyHostToDevice, w.s_in));
+        p->stats.h2d_bytes += sizeof(TaskRecord) * n_units;
+        p->stats.records_copied += n_units;
+    }
     const uint8_t* wave_args = cx.args_full;
     if (cx.host_args) {   // streaming host arguments (contiguous waves only)
-        const uint64_t bytes = wt * d.arg_stride;
-        CK(cudaMemcpyAsync(w.d_args[half], (const uint8_t*)d.args + wave_first * (uint64_t)d.arg_stride, bytes,
-                           cudaMemcpyHostToDevice, w.s_in));
+        uint64_t bytes = wt * d.arg_stride;
+        if (cx.args_limit_bytes) {   // the last task of the map may cover fewer argument items than a full record
+            const uint64_t start = wave_first * (uint64_t)d.arg_stride;
+            bytes = start >= cx.args_limit_bytes ? 0 : std::min(bytes, cx.args_limit_bytes - start);
+        }
+        if (bytes)
+            CK(cudaMemcpyAsync(w.d_args[half], (const uint8_t*)d.args + wave_first * (uint64_t)d.arg_stride, bytes,
+                               cudaMemcpyHostToDevice, w.s_in));
         p->stats.h2d_bytes += bytes;
         wave_args = w.d_args[half];
     }
@@ -511,8 +582,8 @@ static int run_wave(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry& b
 
     // compute streams: dispatch on s_comp; gather on s_comp too, or -- overlapped waves -- on the
     // higher-priority s_gath so that it runs while the next wave's dispatch kernel computes.
-    // Overlapped waves use alternating halves of the ring / header array.
-    const bool ov = cx.overlap;
+    // Overlapped waves use alternating halves of the ring / header array.  Direct waves use neither.
+    const bool ov = cx.overlap && !direct;
     cudaStream_t s_g = ov ? w.s_gath : w.s_comp;
     uint8_t* ring_base = ov ? w.d_ring + (size_t)half * (p->ring_bytes / 2) : w.d_ring;
     SlotHeader* hdr_base = ov ? w.d_headers + (size_t)half * kRecCapacity : w.d_headers;
@@ -522,13 +593,16 @@ static int run_wave(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry& b
     if (wno >= 2) CK(cudaStreamWaitEvent(w.s_comp, w.ev_comp[(wno - 2) % kRecWindows], 0));
     w.prev_wave_overlap = ov;
     if (!cx.full_window) CK(cudaStreamWaitEvent(w.s_comp, w.ev_out[half], 0));  // out half drained
+    uint8_t* const out_window = cx.full_window ? cx.window_base : w.d_out[half];      // ordered output of this wave's window
+    const uint64_t out_first = cx.full_window ? part.first : wave_first;               // map index of out_window[0]
     WaveParams wp;
-    wp.records = drec;
-    wp.headers = hdr_base;
-    wp.ring = ring_base;
+    memset(&wp, 0, sizeof wp);
+    wp.records = have_records ? drec : nullptr;
+    wp.headers = direct ? nullptr : hdr_base;
+    wp.ring = direct ? out_window + (wave_first - out_first) * cx.R : ring_base;
     wp.ticket = w.d_tickets + (wno % kTickets);
     wp.n_units = n_units;
-    wp.slot_stride = cx.slot_stride;
+    wp.slot_stride = direct ? cx.unit * cx.R : cx.slot_stride;
     wp.args = wave_args;
     wp.arg_stride = d.arg_stride;
     wp.index_start = d.index_start;
@@ -539,7 +613,16 @@ static int run_wave(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry& b
     wp.err_word = &w.d_ctrl[slot].err;
     wp.resilient = cx.resilient ? 1u : 0u;
     wp.sum = cx.sum_kind ? &w.d_ctrl[slot].sum : nullptr;
-    int occ_d = (d.arg_stride == 0 && body.kernel_index) ? w.occ_index[st.func_id] : w.occ[st.func_id];
+    wp.sum_hi = cx.sum_kind ? &w.d_ctrl[slot].sum_hi : nullptr;
+    wp.syn_first = wave_first;
+    wp.syn_tasks = wt;
+    wp.syn_arg_off = cx.host_args ? 0 : wave_first * (uint64_t)d.arg_stride;
+    wp.syn_unit = cx.unit;
+    wp.syn_seq = (uint32_t)st.seq;
+    wp.syn_func = (uint32_t)st.func_id;
+    wp.syn_attempt = part.attempt;
+    wp.n_items = d.n_items ? d.n_items : ~0ull;
+    int occ_d = worker_occ(w, st.func_id, body, d.arg_stride == 0);
     if (body.max_ctas_per_sm) occ_d = std::min(occ_d, body.max_ctas_per_sm);
     if (ov && occ_d > 1) occ_d -= 1;     // leave SM slots for the concurrently running gather CTAs
     if (const char* e = getenv("FBR_DISPATCH_OCC")) occ_d = std::max(1, std::min(occ_d, atoi(e)));
@@ -547,87 +630,96 @@ static int run_wave(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry& b
     TimedPair td{nullptr, nullptr}, tg{nullptr, nullptr};
     if (timing) {
         CK(cudaEventCreate(&td.a)); CK(cudaEventCreate(&td.b));
-        CK(cudaEventCreate(&tg.a)); CK(cudaEventCreate(&tg.b));
         CK(cudaEventRecord(td.a, w.s_comp));
     }
-    body.launch(wp, grid_d, w.s_comp);
-    CK(cudaGetLastError());
-    if (timing) CK(cudaEventRecord(td.b, w.s_comp));
-    if (ov) {
-        CK(cudaEventRecord(w.ev_disp[rw], w.s_comp));
-        CK(cudaStreamWaitEvent(s_g, w.ev_disp[rw], 0));
-    }
-    if (timing) CK(cudaEventRecord(tg.a, s_g));
-
-    GatherParams gp;
-    gp.headers = hdr_base;
-    gp.ring = ring_base;
-    gp.n_units = n_units;
-    gp.slot_stride = cx.slot_stride;
-    gp.result_bytes = cx.R;
-    gp.pad = 0;
-    gp.out = cx.full_window ? cx.window_base : w.d_out[half];
-    gp.win_first = cx.full_window ? part.first : wave_first;
-    gp.ticket_to_reset = wp.ticket;
-    gp.lost_count = cx.resilient ? &w.d_ctrl[slot].lost_count : nullptr;
-    gp.lost_units = part.d_lost;
-    gp.lost_capacity = part.lost_cap;
-    const uint64_t total_vec = (uint64_t)n_units * (cx.slot_stride >> 4);
-    const int grid_g = (int)std::max<uint64_t>(1, std::min<uint64_t>((total_vec + kThreads * 4 - 1) / (kThreads * 4),
-                                                                      (uint64_t)w.sm_count * w.occ_gather));
-    // kernel choice for this wave (see kernels.cuh): TMA bulk pipeline, row streaming, or flat
-    const bool aligned = (((uintptr_t)gp.out & 15) == 0) && (((uint64_t)cx.unit * cx.R) == cx.slot_stride);
-    const bool rows_ok = aligned && (cx.slot_stride % 4096 == 0) && getenv("FBR_GATHER_FLAT") == nullptr;
-    const bool bulk_ok = rows_ok && !cx.resilient &&
-                         (cx.slot_stride % bulk::kChunk == 0 || getenv("FBR_BULK_SMALL") != nullptr) &&   // 4 KB slots: rows kernel is faster (37 vs 41 us on the pi wave)
-                         (cx.slot_stride <= bulk::kChunk || cx.slot_stride % bulk::kChunk == 0) &&
-                         !(getenv("FBR_GATHER_BULK") && atoi(getenv("FBR_GATHER_BULK")) == 0);
-    uint32_t* gticket = w.d_tickets + kTickets + (wno % kTickets);   // zero at launch, re-armed below
-    if (bulk_ok) {
-        const uint32_t stage = std::min<uint32_t>(cx.slot_stride, bulk::kChunk);
-        const size_t smem_bytes = (size_t)bulk::kStages * stage;
-        // big chunks: ONE warp per SM saturates HBM (measured 104 % of the copy peak vs 102.5 % with two);
-        // 4 KB chunks need more CTAs to keep enough bytes in flight
-        int per_sm = stage >= bulk::kChunk ? 1 : (int)std::min<size_t>(8, (200u << 10) / smem_bytes);
-        if (const char* e = getenv("FBR_GATHER_OCC")) per_sm = std::max(1, atoi(e));
-        // ~256 KB of ring per ticket (<= 32 slots: one header per lane), >= ~8 tickets per CTA
-        const uint64_t max_ctas = (uint64_t)w.sm_count * per_sm;
-        uint32_t group_slots = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(
-            std::min<uint64_t>(bulk::kGroup, (256u << 10) / cx.slot_stride), n_units / (8 * max_ctas)));
-        if (const char* e = getenv("FBR_BULK_GROUP")) group_slots = std::max(1, std::min(32, atoi(e)));
-        const uint32_t n_groups = (n_units + group_slots - 1) / group_slots;
-        const int grid_b = (int)std::min<uint64_t>(n_groups, max_ctas);
-        gather_bulk_kernel<<<grid_b, 32, smem_bytes, s_g>>>(gp, gticket, stage, group_slots);
-        CK(cudaMemsetAsync(gticket, 0, sizeof(uint32_t), s_g));
-    } else if (rows_ok) {
-        // ~128 KB of ring per ticket, but never fewer than ~4 tickets per resident CTA (small waves);
-        // big slots (>= 32 KB): 4 fat streams per SM measured best (100 % of the copy peak vs 99 %)
-        int occ_g = cx.slot_stride >= (32u << 10) ? std::min(w.occ_gather_rows, 4) : w.occ_gather_rows;
-        if (const char* e = getenv("FBR_GATHER_OCC")) occ_g = std::max(1, std::min(occ_g, atoi(e)));
-        const uint64_t max_ctas = (uint64_t)w.sm_count * occ_g;
-        const uint32_t group_slots = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((128u << 10) / cx.slot_stride, n_units / (4 * max_ctas)));
-        const uint32_t n_groups = (n_units + group_slots - 1) / group_slots;
-        const int grid_r = (int)std::min<uint64_t>(n_groups, max_ctas);
-        // waves that fit the L2 are gathered newest-slot-first (see the kernel); FBR_GATHER_REVERSE=0/1 overrides
-        bool reverse = (uint64_t)n_units * cx.slot_stride <= (128ull << 20);
-        if (const char* e = getenv("FBR_GATHER_REVERSE")) reverse = atoi(e) != 0;
-        gather_rows_kernel<<<grid_r, kThreads, 0, s_g>>>(gp, gticket, group_slots, reverse);
-        CK(cudaMemsetAsync(gticket, 0, sizeof(uint32_t), s_g));
-    } else {
-        gather_ordered_kernel<<<grid_g, kThreads, 0, s_g>>>(gp);
-    }
+    body.launch(&wp, grid_d, (void*)w.s_comp);
     CK(cudaGetLastError());
     if (timing) {
-        CK(cudaEventRecord(tg.b, s_g));
+        CK(cudaEventRecord(td.b, w.s_comp));
         part.t_dispatch.push_back(td);
-        part.t_gather.push_back(tg);
     }
-    CK(cudaEventRecord(w.ev_comp[rw], s_g));
     p->stats.dispatch_launches++;
-    p->stats.gather_launches++;
     p->stats.units_dispatched += n_units;
-    p->stats.gather_bytes += 2 * wt * cx.R;
     p->stats.dispatch_bytes += wt * ((uint64_t)(d.arg_stride ? body.arg_bytes : 0) + cx.R);
+
+    if (direct) {
+        p->stats.direct_waves++;
+        CK(cudaEventRecord(w.ev_comp[rw], w.s_comp));
+    } else {
+        if (ov) {
+            CK(cudaEventRecord(w.ev_disp[rw], w.s_comp));
+            CK(cudaStreamWaitEvent(s_g, w.ev_disp[rw], 0));
+        }
+        if (timing) {
+            CK(cudaEventCreate(&tg.a)); CK(cudaEventCreate(&tg.b));
+            CK(cudaEventRecord(tg.a, s_g));
+        }
+        GatherParams gp;
+        gp.headers = hdr_base;
+        gp.ring = ring_base;
+        gp.n_units = n_units;
+        gp.slot_stride = cx.slot_stride;
+        gp.result_bytes = cx.R;
+        gp.pad = 0;
+        gp.out = out_window;
+        gp.win_first = out_first;
+        gp.ticket_to_reset = nullptr;     // dispatch kernels re-arm their own ticket (TicketClaimer::rearm)
+        gp.lost_count = cx.resilient ? &w.d_ctrl[slot].lost_count : nullptr;
+        gp.lost_units = part.d_lost;
+        gp.lost_capacity = part.lost_cap;
+        const uint64_t total_vec = (uint64_t)n_units * (cx.slot_stride >> 4);
+        const int grid_g = (int)std::max<uint64_t>(1, std::min<uint64_t>((total_vec + kThreads * 4 - 1) / (kThreads * 4),
+                                                                          (uint64_t)w.sm_count * w.occ_gather));
+        // kernel choice for this wave (see kernels.cuh): TMA bulk pipeline, row streaming, or flat
+        const bool aligned = (((uintptr_t)gp.out & 15) == 0) && (((uint64_t)cx.unit * cx.R) == cx.slot_stride);
+        const bool rows_ok = aligned && (cx.slot_stride % 4096 == 0) && getenv("FBR_GATHER_FLAT") == nullptr;
+        const bool bulk_ok = rows_ok && !cx.resilient &&
+                             (cx.slot_stride % bulk::kChunk == 0 || getenv("FBR_BULK_SMALL") != nullptr) &&   // 4 KB slots: rows kernel is faster (37 vs 41 us on the pi wave)
+                             (cx.slot_stride <= bulk::kChunk || cx.slot_stride % bulk::kChunk == 0) &&
+                             !(getenv("FBR_GATHER_BULK") && atoi(getenv("FBR_GATHER_BULK")) == 0);
+        uint32_t* gticket = w.d_tickets + kTickets + (wno % kTickets);   // zero at launch, re-armed below
+        if (bulk_ok) {
+            const uint32_t stage = std::min<uint32_t>(cx.slot_stride, bulk::kChunk);
+            const size_t smem_bytes = (size_t)bulk::kStages * stage;
+            // big chunks: ONE warp per SM saturates HBM (measured 104 % of the copy peak vs 102.5 % with two);
+            // 4 KB chunks need more CTAs to keep enough bytes in flight
+            int per_sm = stage >= bulk::kChunk ? 1 : (int)std::min<size_t>(8, (200u << 10) / smem_bytes);
+            if (const char* e = getenv("FBR_GATHER_OCC")) per_sm = std::max(1, atoi(e));
+            // ~256 KB of ring per ticket (<= 32 slots: one header per lane), >= ~8 tickets per CTA
+            const uint64_t max_ctas = (uint64_t)w.sm_count * per_sm;
+            uint32_t group_slots = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(
+                std::min<uint64_t>(bulk::kGroup, (256u << 10) / cx.slot_stride), n_units / (8 * max_ctas)));
+            if (const char* e = getenv("FBR_BULK_GROUP")) group_slots = std::max(1, std::min(32, atoi(e)));
+            const uint32_t n_groups = (n_units + group_slots - 1) / group_slots;
+            const int grid_b = (int)std::min<uint64_t>(n_groups, max_ctas);
+            gather_bulk_kernel<<<grid_b, 32, smem_bytes, s_g>>>(gp, gticket, stage, group_slots);
+            CK(cudaMemsetAsync(gticket, 0, sizeof(uint32_t), s_g));
+        } else if (rows_ok) {
+            // ~128 KB of ring per ticket, but never fewer than ~4 tickets per resident CTA (small waves);
+            // big slots (>= 32 KB): 4 fat streams per SM measured best (100 % of the copy peak vs 99 %)
+            int occ_g = cx.slot_stride >= (32u << 10) ? std::min(w.occ_gather_rows, 4) : w.occ_gather_rows;
+            if (const char* e = getenv("FBR_GATHER_OCC")) occ_g = std::max(1, std::min(occ_g, atoi(e)));
+            const uint64_t max_ctas = (uint64_t)w.sm_count * occ_g;
+            const uint32_t group_slots = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((128u << 10) / cx.slot_stride, n_units / (4 * max_ctas)));
+            const uint32_t n_groups = (n_units + group_slots - 1) / group_slots;
+            const int grid_r = (int)std::min<uint64_t>(n_groups, max_ctas);
+            // waves that fit the L2 are gathered newest-slot-first (see the kernel); FBR_GATHER_REVERSE=0/1 overrides
+            bool reverse = (uint64_t)n_units * cx.slot_stride <= (128ull << 20);
+            if (const char* e = getenv("FBR_GATHER_REVERSE")) reverse = atoi(e) != 0;
+            gather_rows_kernel<<<grid_r, kThreads, 0, s_g>>>(gp, gticket, group_slots, reverse);
+            CK(cudaMemsetAsync(gticket, 0, sizeof(uint32_t), s_g));
+        } else {
+            gather_ordered_kernel<<<grid_g, kThreads, 0, s_g>>>(gp);
+        }
+        CK(cudaGetLastError());
+        if (timing) {
+            CK(cudaEventRecord(tg.b, s_g));
+            part.t_gather.push_back(tg);
+        }
+        CK(cudaEventRecord(w.ev_comp[rw], s_g));
+        p->stats.gather_launches++;
+        p->stats.gather_bytes += 2 * wt * cx.R;
+    }
 
     // copy-out stream (streaming parts): D2H of the ordered window of this wave
     if (contiguous) {
@@ -640,7 +732,7 @@ static int run_wave(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry& b
             CK(cudaEventRecord(w.ev_out[half], w.s_out));
             CK(cudaEventRecord(wd, w.s_out));
         } else {
-            CK(cudaEventRecord(wd, s_g));
+            CK(cudaEventRecord(wd, direct ? w.s_comp : s_g));
         }
         part.wave_done.push_back(wd);
     }
@@ -662,8 +754,9 @@ static int finish_round(fbr_pool* p, SeqState& st, SeqPart& part, bool copy_wind
     CK(cudaMemcpyAsync(&w.h_ctrl[slot], &w.d_ctrl[slot], sizeof(SeqCtrl), cudaMemcpyDeviceToHost, w.s_out));
     if (cx.resilient && part.lost_cap)
         CK(cudaMemcpyAsync(part.h_lost, part.d_lost, sizeof(LostUnit) * part.lost_cap, cudaMemcpyDeviceToHost, w.s_out));
-    if (part.done) CK(cudaEventDestroy(part.done));
-    CK(cudaEventCreateWithFlags(&part.done, cudaEventDisableTiming));
+    // one event per part for its whole life, re-recorded every round: another waiter may hold the handle
+    // (fbr_result_wait blocks on it outside the pool lock), so it must never be destroyed under it
+    if (!part.done) CK(cudaEventCreateWithFlags(&part.done, cudaEventDisableTiming));
     CK(cudaEventRecord(part.done, w.s_out));
     return FBR_OK;
 }
@@ -708,16 +801,23 @@ static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry
         }
     }
 
+    if (d.n_items && d.arg_stride && body.result_kind == FBR_RES_BITS8)
+        cx.args_limit_bytes = d.n_items * (uint64_t)(d.arg_stride / 8);   // a byte-task's record is 8 items
     // arguments that stay device-resident for the whole map
     if (cx.args_dev) {
         cx.args_full = (const uint8_t*)d.args;
     } else if (cx.resilient && d.arg_stride) {
         // lost units may be re-dispatched at any time: keep every argument record on the device
         CK(cudaMallocAsync(&part.d_args_full, std::max<uint64_t>(16, st.n_tasks * (uint64_t)d.arg_stride), w.s_in));
-        CK(cudaMemcpyAsync((uint8_t*)part.d_args_full + part.first * (uint64_t)d.arg_stride,
-                           (const uint8_t*)d.args + part.first * (uint64_t)d.arg_stride, part.count * (uint64_t)d.arg_stride,
-                           cudaMemcpyHostToDevice, w.s_in));
-        p->stats.h2d_bytes += part.count * (uint64_t)d.arg_stride;
+        uint64_t abytes = part.count * (uint64_t)d.arg_stride;
+        if (cx.args_limit_bytes) {
+            const uint64_t start = part.first * (uint64_t)d.arg_stride;
+            abytes = start >= cx.args_limit_bytes ? 0 : std::min(abytes, cx.args_limit_bytes - start);
+        }
+        if (abytes)
+            CK(cudaMemcpyAsync((uint8_t*)part.d_args_full + part.first * (uint64_t)d.arg_stride,
+                               (const uint8_t*)d.args + part.first * (uint64_t)d.arg_stride, abytes, cudaMemcpyHostToDevice, w.s_in));
+        p->stats.h2d_bytes += abytes;
         cx.args_full = (const uint8_t*)part.d_args_full;
     }
 
@@ -727,8 +827,19 @@ static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry
     // 0.3837 vs 0.3876 ms/step -- the gather is only 9 % of the step and the two kernels contend for
     // SM slots, so it is off by default.
     cx.overlap = cx.full_window && !cx.resilient && (p->flags & FBR_POOL_OVERLAP) != 0;
+    // Direct placement: a contiguous, unshuffled, non-resilient block needs neither task records nor the
+    // ring -- unit t of a wave is tasks [wave_first + t*unit, ...) and its results belong at exactly that
+    // index of the ordered window, so the dispatch kernel stores them there and no gather is launched.
+    // (Shuffled arrival, several attempts per unit and FBR_VIA_RING keep the ring + gather_ordered path.)
+    {
+        static const bool env_off = getenv("FBR_DIRECT") && atoi(getenv("FBR_DIRECT")) == 0;
+        const bool unit_ok = ((uint64_t)unit * R) % 16 == 0 || unit == 1;   // full vectors are stored 16 B at a time
+        const bool base_ok = !cx.out_dev || (((uintptr_t)d.out + part.first * R) & 15) == 0;
+        cx.direct = !env_off && !cx.resilient && !(d.flags & (FBR_SHUFFLE | FBR_VIA_RING)) && unit_ok && base_ok;
+    }
     // wave capacity in claim units
-    uint64_t units_cap = std::min<uint64_t>(kRecCapacity, (cx.overlap ? p->ring_bytes / 2 : p->ring_bytes) / cx.slot_stride);
+    uint64_t units_cap = cx.direct ? (1ull << 31) / std::max<uint32_t>(1, cx.slot_stride) :   // 32-bit unit counter
+        std::min<uint64_t>(kRecCapacity, (cx.overlap ? p->ring_bytes / 2 : p->ring_bytes) / cx.slot_stride);
     if (cx.host_args) units_cap = std::min<uint64_t>(units_cap, p->ring_bytes / ((uint64_t)unit * d.arg_stride));
     if (!cx.full_window) units_cap = std::min<uint64_t>(units_cap, p->ring_bytes / ((uint64_t)unit * R));
     if (units_cap == 0) return fail(FBR_ENOMEM, "ring_bytes=%llu too small for one claim unit of %u tasks", (unsigned long long)p->ring_bytes, unit);
@@ -770,7 +881,7 @@ static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry
     }
 
     if (d.flags & FBR_WANT_SUM) {
-        if (!(body.flags & FBR_BODY_SUMMABLE)) return fail(FBR_EINVAL, "body %s results cannot be summed", body.name);
+        if (!(body.flags & FBR_BODY_SUMMABLE)) return fail(FBR_EINVAL, "body %s results cannot be summed", body.name.c_str());
         cx.sum_kind = 1;   // the dispatch kernel folds sum(results) while they are in registers
     }
 
@@ -782,22 +893,27 @@ static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry
         const int rw = (int)(wno % kRecWindows);
         const uint64_t wave_first = part.first + done_tasks;  // map index of the wave's first task
 
-        // task records into the pinned ring window (the host may not overwrite a window whose
-        // previous H2D is still in flight)
-        CK(cudaEventSynchronize(w.ev_rec_h2d[rw]));
-        TaskRecord* hrec = w.h_records + (size_t)rw * kRecCapacity;
-        for (uint32_t u = 0; u < n_units; ++u) {
-            const uint64_t off = (uint64_t)u * unit;
-            TaskRecord& r = hrec[u];
-            r.seq = (uint32_t)st.seq;
-            r.count = (uint32_t)std::min<uint64_t>(unit, wt - off);
-            r.first = wave_first + off;
-            r.arg_off = cx.host_args ? off * (uint64_t)d.arg_stride : (wave_first + off) * (uint64_t)d.arg_stride;
-            r.func_id = (uint32_t)st.func_id;
-            r.attempt = 0;
+        // Task records go through the pinned ring window only when they are not an arithmetic
+        // progression the kernels can compute (shuffled arrival), or when FBR_RECORDS=1 asks for the
+        // explicit-record path.  (The host may not overwrite a window whose previous H2D is in flight.)
+        static const bool env_records = getenv("FBR_RECORDS") && atoi(getenv("FBR_RECORDS")) != 0;
+        const bool have_records = (d.flags & FBR_SHUFFLE) || env_records;
+        if (have_records) {
+            CK(cudaEventSynchronize(w.ev_rec_h2d[rw]));
+            TaskRecord* hrec = w.h_records + (size_t)rw * kRecCapacity;
+            for (uint32_t u = 0; u < n_units; ++u) {
+                const uint64_t off = (uint64_t)u * unit;
+                TaskRecord& r = hrec[u];
+                r.seq = (uint32_t)st.seq;
+                r.count = (uint32_t)std::min<uint64_t>(unit, wt - off);
+                r.first = wave_first + off;
+                r.arg_off = cx.host_args ? off * (uint64_t)d.arg_stride : (wave_first + off) * (uint64_t)d.arg_stride;
+                r.func_id = (uint32_t)st.func_id;
+                r.attempt = part.attempt;
+            }
+            if (d.flags & FBR_SHUFFLE) shuffle_records(hrec, n_units, d.shuffle_seed ^ (wno * 0x9E3779B97F4A7C15ull));
         }
-        if (d.flags & FBR_SHUFFLE) shuffle_records(hrec, n_units, d.shuffle_seed ^ (wno * 0x9E3779B97F4A7C15ull));
-        int rc = run_wave(p, st, part, body, n_units, wave_first, wt, true, wno);
+        int rc = run_wave(p, st, part, body, n_units, wave_first, wt, true, have_records, wno);
         if (rc != FBR_OK) return rc;
         done_tasks += wt;
         part.wave_cum.push_back(done_tasks);
@@ -813,7 +929,7 @@ static int resilient_advance(fbr_pool* p, SeqState& st, SeqPart& part) {
     if (!part.cx.resilient || part.finalized) return 0;
     Worker& w = p->workers[part.worker];
     CK(cudaSetDevice(w.device));
-    const BodyEntry& body = kBodies[st.func_id];
+    const BodyEntry& body = *body_of(st.func_id);
     const uint32_t lost = std::min(w.h_ctrl[part.ctrl_slot].lost_count, part.lost_cap);
     if (lost == 0) {
         part.finalized = true;
@@ -845,7 +961,7 @@ static int resilient_advance(fbr_pool* p, SeqState& st, SeqPart& part) {
             r.attempt = part.attempt;
             wt += l.count;
         }
-        int rc = run_wave(p, st, part, body, n_units, 0, wt, false, wno);
+        int rc = run_wave(p, st, part, body, n_units, 0, wt, false, true, wno);
         if (rc != FBR_OK) return rc;
     }
     int rc = finish_round(p, st, part, false);
@@ -886,9 +1002,10 @@ int fbr_abi_version(void) { return FBR_ABI_VERSION; }
 int fbr_internal_preload(int device) {
     if (cudaSetDevice(device) != cudaSuccess) return FBR_ECUDA;
     cudaFuncAttributes at;
-    for (int f = 0; f < F_COUNT; ++f) {
-        cudaFuncGetAttributes(&at, kBodies[f].kernel);
-        if (kBodies[f].kernel_index) cudaFuncGetAttributes(&at, kBodies[f].kernel_index);
+    for (int f = 0, n = body_count(); f < n; ++f) {   // asking for the occupancy loads the kernels
+        const BodyEntry& b = *body_of(f);
+        b.occupancy(0);
+        if (b.flags & FBR_BODY_INDEX_ARG) b.occupancy(1);
     }
     cudaFuncGetAttributes(&at, (const void*)gather_ordered_kernel);
     cudaFuncGetAttributes(&at, (const void*)gather_rows_kernel);
@@ -915,13 +1032,14 @@ int fbr_device_count(int* n) {
 
 int fbr_body_count(int* n) {
     if (!n) return fail(FBR_EINVAL, "n is NULL");
-    *n = F_COUNT;
+    *n = body_count();
     return FBR_OK;
 }
 
 int fbr_body_info(int func_id, fbr_body_info_t* info) {
-    if (!info || func_id < 0 || func_id >= F_COUNT) return fail(FBR_EINVAL, "bad func_id %d", func_id);
-    const BodyEntry& b = kBodies[func_id];
+    const BodyEntry* bp = body_of(func_id);
+    if (!info || !bp) return fail(FBR_EINVAL, "bad func_id %d", func_id);
+    const BodyEntry& b = *bp;
     memset(info, 0, sizeof *info);
     info->func_id = func_id;
     info->arg_bytes = b.arg_bytes;
@@ -929,22 +1047,67 @@ int fbr_body_info(int func_id, fbr_body_info_t* info) {
     info->result_kind = b.result_kind;
     info->flags = b.flags;
     info->unit_tasks = b.unit_tasks;
-    snprintf(info->name, sizeof info->name, "%s", b.name);
+    snprintf(info->name, sizeof info->name, "%s", b.name.c_str());
     return FBR_OK;
 }
 
 int fbr_body_lookup(const char* name, int* func_id) {
     if (!name || !func_id) return fail(FBR_EINVAL, "NULL argument");
-    for (int f = 0; f < F_COUNT; ++f)
-        if (strcmp(kBodies[f].name, name) == 0) { *func_id = f; return FBR_OK; }
-    return fail(FBR_ENOENT, "no device body named '%s' is compiled into libfiber_b200", name);
+    for (int f = 0, n = body_count(); f < n; ++f)
+        if (body_of(f)->name == name) { *func_id = f; return FBR_OK; }
+    return fail(FBR_ENOENT, "no device body named '%s' is compiled into libfiber_b200 or registered with fbr_register_body", name);
+}
+
+int fbr_register_body(const char* name, const char* module_path, const char* entry, int* func_id) {
+    if (!name || !module_path || !entry || !func_id) return fail(FBR_EINVAL, "NULL argument");
+    // RTLD_LOCAL: several body modules may define the same helper symbols
+    void* h = dlopen(module_path, RTLD_NOW | RTLD_LOCAL);
+    if (!h) return fail(FBR_ENOENT, "dlopen(%s) failed: %s", module_path, dlerror());
+    fbr_body_entry_fn fn = (fbr_body_entry_fn)dlsym(h, entry);
+    if (!fn) {
+        dlclose(h);
+        return fail(FBR_ENOENT, "module %s has no entry point '%s'", module_path, entry);
+    }
+    const fbr_body_module_t* m = fn();
+    if (!m || m->abi != FBR_BODY_MODULE_ABI || m->wave_params_bytes != sizeof(WaveParams) || !m->launch || !m->occupancy || !m->name) {
+        const unsigned abi = m ? m->abi : 0u, wpb = m ? m->wave_params_bytes : 0u;
+        dlclose(h);
+        return fail(FBR_EINVAL, "module %s: descriptor ABI %u / wave-parameter size %u do not match this library (%u / %u); rebuild it against include/fiber_b200_body.cuh",
+                    module_path, abi, wpb, (unsigned)FBR_BODY_MODULE_ABI, (unsigned)sizeof(WaveParams));
+    }
+    if (strcmp(m->name, name) != 0) {
+        dlclose(h);
+        return fail(FBR_EINVAL, "module %s exports body '%s', not '%s'", module_path, m->name, name);
+    }
+    if (m->result_bytes == 0 || m->unit_tasks == 0 || (m->arg_bytes % 8) != 0 || m->result_kind > FBR_RES_BITS8) {
+        dlclose(h);
+        return fail(FBR_EINVAL, "module %s: body '%s' has an invalid record layout", module_path, name);
+    }
+    std::lock_guard<std::mutex> g(g_body_mu);
+    builtin_bodies_once();
+    for (size_t f = 0; f < g_bodies.size(); ++f)
+        if (g_bodies[f].name == name) {
+            if (g_bodies[f].module == nullptr) { dlclose(h); return fail(FBR_EINVAL, "'%s' is a compiled-in body", name); }
+            dlclose(h);             // same name registered before: idempotent, keep the first module
+            *func_id = (int)f;
+            return FBR_OK;
+        }
+    BodyEntry b;
+    b.name = name;
+    b.arg_bytes = m->arg_bytes; b.result_bytes = m->result_bytes; b.result_kind = m->result_kind;
+    b.flags = m->flags; b.unit_tasks = m->unit_tasks;
+    b.launch = m->launch; b.occupancy = m->occupancy;
+    b.module = h;
+    g_bodies.push_back(b);
+    *func_id = (int)g_bodies.size() - 1;
+    return FBR_OK;
 }
 
 int fbr_plan_query(int func_id, uint64_t n_tasks, uint32_t chunksize, uint64_t ring_bytes, int n_workers,
                    int worker, int sm_count, fbr_plan_t* plan) {
-    if (!plan || func_id < 0 || func_id >= F_COUNT || n_workers < 1 || worker < 0 || worker >= n_workers)
+    if (!plan || !body_of(func_id) || n_workers < 1 || worker < 0 || worker >= n_workers)
         return fail(FBR_EINVAL, "bad arguments");
-    const BodyEntry& body = kBodies[func_id];
+    const BodyEntry& body = *body_of(func_id);
     const uint64_t ring = round_up(ring_bytes ? ring_bytes : (256ull << 20), 4096);
     const uint32_t cs = chunksize ? chunksize : 32u;
     if (sm_count <= 0) sm_count = 148;
@@ -1105,31 +1268,31 @@ int fbr_map_submit(fbr_pool_t* p, const fbr_map_desc_t* d, uint64_t* seq_out) {
     if (!p || !d || !seq_out) return fail(FBR_EINVAL, "NULL argument");
     std::lock_guard<std::mutex> g(p->mu);
     if (p->state != ST_RUN) return fail(FBR_ESTATE, "Pool is not running");
-    if (d->func_id < 0 || d->func_id >= F_COUNT) return fail(FBR_EINVAL, "bad func_id %d", d->func_id);
-    const BodyEntry& body = kBodies[d->func_id];
+    if (!body_of(d->func_id)) return fail(FBR_EINVAL, "bad func_id %d", d->func_id);
+    const BodyEntry& body = *body_of(d->func_id);
     const bool dev_mode = (d->flags & (FBR_ARGS_DEVICE | FBR_OUT_DEVICE)) != 0;
     if (dev_mode && p->workers.size() != 1 && !p->peer_ok)
         return fail(FBR_EINVAL, "device-resident args/out on a multi-worker pool need peer access between all its GPUs");
     if (d->arg_stride == 0) {
         if (!(body.flags & FBR_BODY_INDEX_ARG))
-            return fail(FBR_EINVAL, "body %s needs explicit argument records (arg_stride=0)", body.name);
+            return fail(FBR_EINVAL, "body %s needs explicit argument records (arg_stride=0)", body.name.c_str());
     } else if (body.flags & FBR_BODY_INDEX_ONLY) {
-        return fail(FBR_EINVAL, "body %s takes range() arguments only (arg_stride must be 0)", body.name);
+        return fail(FBR_EINVAL, "body %s takes range() arguments only (arg_stride must be 0)", body.name.c_str());
     } else {
         if (d->arg_stride < body.arg_bytes || (d->arg_stride % 8) != 0)
-            return fail(FBR_EINVAL, "arg_stride %u invalid for body %s (arg_bytes %u)", d->arg_stride, body.name, body.arg_bytes);
+            return fail(FBR_EINVAL, "arg_stride %u invalid for body %s (arg_bytes %u)", d->arg_stride, body.name.c_str(), body.arg_bytes);
         if (d->n_tasks && !d->args) return fail(FBR_EINVAL, "args is NULL");
-        if (body.arg_bytes >= 16 && (d->arg_stride % 16 || ((uintptr_t)d->args % 16)))
-            return fail(FBR_EINVAL, "argument records of body %s must be 16-byte aligned", body.name);
+        if (body.arg_bytes >= 16 && body.result_kind != FBR_RES_BITS8 && (d->arg_stride % 16 || ((uintptr_t)d->args % 16)))
+            return fail(FBR_EINVAL, "argument records of body %s must be 16-byte aligned", body.name.c_str());
     }
     if ((body.flags & FBR_BODY_NEEDS_SHARED) && (!d->shared || d->shared_bytes < sizeof(ParzenShared)))
-        return fail(FBR_EINVAL, "body %s needs a shared argument block", body.name);
+        return fail(FBR_EINVAL, "body %s needs a shared argument block", body.name.c_str());
     if ((d->flags & FBR_OUT_DEVICE) && !d->out) return fail(FBR_EINVAL, "FBR_OUT_DEVICE without out");
     if ((d->flags & FBR_RESULTS_ON_DEVICE) && ((d->flags & FBR_OUT_DEVICE) || d->out))
         return fail(FBR_EINVAL, "FBR_RESULTS_ON_DEVICE owns its output buffer: do not pass out / FBR_OUT_DEVICE");
     if ((d->flags & FBR_RESILIENT) && (d->flags & FBR_SHUFFLE)) return fail(FBR_EINVAL, "FBR_RESILIENT cannot be combined with FBR_SHUFFLE");
     if ((d->flags & FBR_WANT_SUM) && !(body.flags & FBR_BODY_SUMMABLE))
-        return fail(FBR_EINVAL, "body %s results cannot be summed", body.name);
+        return fail(FBR_EINVAL, "body %s results cannot be summed", body.name.c_str());
 
     std::unique_ptr<SeqState> st(new SeqState());
     st->seq = ++p->next_seq;
@@ -1189,11 +1352,14 @@ int fbr_map_submit(fbr_pool_t* p, const fbr_map_desc_t* d, uint64_t* seq_out) {
 static void harvest(fbr_pool* p, SeqState& st) {
     if (st.finished) return;
     st.sum = 0;
+    st.sum_lo = 0;
+    st.sum_hi = 0;
     unsigned long long err = ~0ull;
     for (auto& part : st.parts) {
         Worker& w = p->workers[part.worker];
         const SeqCtrl& c = w.h_ctrl[part.ctrl_slot];
-        st.sum += c.sum;
+        st.sum_lo += (uint64_t)c.sum;       // < 2^32 per task: cannot wrap below 2^32 tasks
+        st.sum_hi += c.sum_hi;
         err = std::min(err, c.err);
         for (auto& t : part.t_dispatch) {
             float ms = 0;
@@ -1203,6 +1369,11 @@ static void harvest(fbr_pool* p, SeqState& st) {
             float ms = 0;
             if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) p->stats.gather_ms += ms;
         }
+    }
+    {
+        const __int128 total = (__int128)st.sum_hi * ((__int128)1 << 32) + (__int128)st.sum_lo;
+        st.sum = (int64_t)(uint64_t)total;
+        st.sum_overflow = total != (__int128)st.sum;
     }
     if (err != ~0ull) {
         st.err_code = (uint32_t)(err & 0xff);
@@ -1260,10 +1431,13 @@ int fbr_result_wait(fbr_pool_t* p, uint64_t seq, int timeout_ms, fbr_result_t* r
         res->result_kind = st.result_kind;
         res->data = st.out;
         res->sum = st.sum;
+        res->sum_lo = st.sum_lo;
+        res->sum_hi = st.sum_hi;
+        res->sum_overflow = st.sum_overflow ? 1u : 0u;
         res->err_code = st.err_code;
         res->err_task = st.err_task;
         res->n_waves = st.n_waves;
-        if (st.err_code) return fail(FBR_ETASK, "task %llu failed with code %u in body %s", (unsigned long long)st.err_task, st.err_code, kBodies[st.func_id].name);
+        if (st.err_code) return fail(FBR_ETASK, "task %llu failed with code %u in body %s", (unsigned long long)st.err_task, st.err_code, body_of(st.func_id)->name.c_str());
         return FBR_OK;
     }
 }

@@ -22,6 +22,7 @@
 #include <string>
 #include <thread>
 #include <unordered_map>
+#include <unordered_set>
 
 #include "../../include/fiber_b200.h"
 #include "bodies.cuh"
@@ -162,6 +163,7 @@ struct fbr_express {
     unsigned long long next_ticket = 0;      // == req_head
     unsigned long long collected = 0;        // responses consumed from the lane
     std::unordered_map<unsigned long long, XResponse> parked;
+    std::unordered_set<unsigned long long> abandoned;   // tickets whose handle was dropped before the response arrived
     unsigned long long idle_ns = 2000000ull; // 2 ms
     uint64_t launches = 0;
 };
@@ -228,7 +230,7 @@ int fbr_express_submit(fbr_express_t* x, int func_id, const void* arg, uint32_t 
         if (x->collected < rh) {
             XResponse r;
             memcpy(&r, (const void*)&L->rsp[x->collected & (kXCap - 1)], sizeof r);
-            x->parked[r.ticket] = r;
+            if (!x->abandoned.erase(r.ticket)) x->parked[r.ticket] = r;
             x->collected++;
             continue;
         }
@@ -263,7 +265,7 @@ int fbr_express_wait(fbr_express_t* x, uint64_t ticket, void* result, uint32_t* 
                     XResponse r;
                     memcpy(&r, (const void*)&L->rsp[x->collected & (kXCap - 1)], sizeof r);
                     x->collected++;
-                    x->parked[r.ticket] = r;
+                    if (!x->abandoned.erase(r.ticket)) x->parked[r.ticket] = r;
                 }
                 it = x->parked.find(ticket);
             }
@@ -285,6 +287,14 @@ int fbr_express_wait(fbr_express_t* x, uint64_t ticket, void* result, uint32_t* 
         if (timeout_ms >= 0 && std::chrono::steady_clock::now() >= deadline) return xfail(FBR_ETIMEOUT, "express response timeout");
         if (++spins > 20000) std::this_thread::sleep_for(std::chrono::microseconds(20));
     }
+}
+
+/* The caller dropped its handle on `ticket` without waiting: forget the response (now or when it arrives). */
+int fbr_express_discard(fbr_express_t* x, uint64_t ticket) {
+    if (!x) return xfail(FBR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> g(x->mu);
+    if (x->parked.erase(ticket) == 0 && ticket < x->next_ticket) x->abandoned.insert(ticket);
+    return FBR_OK;
 }
 
 int fbr_express_stats(fbr_express_t* x, uint64_t* served, uint64_t* launches, int* resident) {

@@ -48,9 +48,12 @@ static_assert(sizeof(SlotHeader) == 16, "slot header layout is part of the ABI")
 constexpr uint32_t kUnitLost = 0x80000000u;
 
 struct WaveParams {
-    const TaskRecord* records;  // device task ring window of this wave
-    SlotHeader* headers;        // result ring headers (paired with records by ticket)
-    uint8_t* ring;              // result ring payload arena
+    const TaskRecord* records;  // device task ring window of this wave; nullptr: the wave is a contiguous,
+                                // unshuffled block and unit t's record is computed from the syn_* fields below
+                                // (an arithmetic progression needs no 32 B/unit of PCIe traffic)
+    SlotHeader* headers;        // result ring headers (paired with records by ticket); nullptr: direct placement --
+                                // `ring` IS the ordered output window and slot t lands at its final index, no gather
+    uint8_t* ring;              // result ring payload arena (or the ordered output window, see headers)
     uint32_t* ticket;           // device counter, zero at launch
     uint32_t n_units;
     uint32_t slot_stride;       // bytes, multiple of 16
@@ -62,8 +65,39 @@ struct WaveParams {
     uint64_t shared_bytes;
     unsigned long long* err_word;
     uint32_t resilient;         // lost units are re-dispatched by the host (else a fault is an error)
-    long long* sum;             // fold sum(results) here (nullptr: no fold); done where the values are in registers
+    long long* sum;             // fold sum(results) here (nullptr: no fold); done where the values are in registers.
+                                // 8-byte results: sum of the LOW 32-bit halves (as unsigned) ...
+    long long* sum_hi;          // ... and sum of the high halves (arithmetic >> 32) here: the exact, unbounded sum
+                                // is sum_hi * 2^32 + sum, whatever the int64 total would have wrapped to
+    // synthesised records (records == nullptr): unit t = tasks [syn_first + t*syn_unit, ...) of map syn_seq
+    uint64_t syn_first;         // map index of the wave's first task
+    uint64_t syn_tasks;         // tasks in the wave
+    uint64_t syn_arg_off;       // arg_off of unit 0
+    uint32_t syn_unit;          // tasks per unit
+    uint32_t syn_seq;
+    uint32_t syn_func;
+    uint32_t syn_attempt;       // re-dispatch count of the whole wave (a dead worker's block re-run elsewhere)
+    uint64_t n_items;           // bodies whose task consumes several argument items (bit-packed bool twins: 8 per
+                                // task): number of items of the whole map, items at or past it are not read
 };
+
+// Task record of ticket t: from the device task ring, or computed (contiguous wave).
+__device__ __forceinline__ TaskRecord wave_record(const WaveParams& wp, uint32_t t) {
+    if (wp.records != nullptr) return wp.records[t];
+    const uint64_t off = (uint64_t)t * wp.syn_unit;
+    const uint64_t left = wp.syn_tasks - off;
+    TaskRecord r;
+    r.seq = wp.syn_seq;
+    r.count = left < (uint64_t)wp.syn_unit ? (uint32_t)left : wp.syn_unit;
+    r.first = wp.syn_first + off;
+    r.arg_off = wp.syn_arg_off + off * (uint64_t)wp.arg_stride;
+    r.func_id = wp.syn_func;
+    r.attempt = wp.syn_attempt;
+    return r;
+}
+__device__ __forceinline__ void put_header(const WaveParams& wp, uint32_t t, const SlotHeader& h) {
+    if (wp.headers != nullptr) wp.headers[t] = h;
+}
 
 // ------------------------------------------------------------------------------------------------
 // streaming 16 B accesses
@@ -89,6 +123,13 @@ struct TicketClaimer {
         __syncthreads();
         return *s_slot;
     }
+    // Re-arm the counter for the wave that uses it next.  Every CTA draws exactly two tickets >= n_units (the
+    // one that ends its loop and the one prefetched behind it), so n_units + 2*gridDim.x atomics happen in
+    // all, and the highest value is always a prefetched, unused one: its holder knows every other atomic
+    // has been performed and zeroes the counter (no memset node, no gather kernel needed for it).
+    __device__ __forceinline__ void rearm(uint32_t n_units) {
+        if (threadIdx.x == 0 && next == n_units + 2u * gridDim.x - 1u) *counter = 0u;
+    }
     // one-barrier variant: `s_slots[2]` is indexed by iteration parity (see dispatch_thread_kernel)
     __device__ __forceinline__ uint32_t claim_db(uint32_t* s_slots, uint32_t iter) {
         if (threadIdx.x == 0) {
@@ -103,10 +144,11 @@ struct TicketClaimer {
 // Fold one value per thread into a global accumulator: warp shuffle, then one atomic per warp (no
 // block barrier: a __syncthreads() after the persistent loop made ptxas restructure the whole loop,
 // +15 % instructions on the pi body).
-__device__ __forceinline__ void warp_add(long long v, long long* target) {
+// (unsigned arithmetic throughout: two's-complement wrap-around is defined, signed overflow is not)
+__device__ __forceinline__ void warp_add(unsigned long long v, long long* target) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0 && v != 0) atomicAdd(reinterpret_cast<unsigned long long*>(target), (unsigned long long)v);
+    if ((threadIdx.x & 31) == 0 && v != 0) atomicAdd(reinterpret_cast<unsigned long long*>(target), v);
 }
 
 // ================================================================================================
@@ -117,7 +159,8 @@ __device__ __forceinline__ void warp_add(long long v, long long* target) {
 // vt, vt + kThreads, ...  Adds the slice's results to unit_acc / unit_acc32.
 template <class B, bool kIndex>
 __device__ __forceinline__ void run_unit_slice(const WaveParams& wp, const TaskRecord& rec, uint8_t* slot, uint32_t vt,
-                                               const ErrSink& es, long long& unit_acc, uint32_t& unit_acc32) {
+                                               const ErrSink& es, unsigned long long& unit_acc, unsigned long long& unit_hi,
+                                               uint32_t& unit_acc32) {
     using Arg = typename B::Arg;
     using Res = typename B::Res;
     constexpr int V = (sizeof(Res) >= 16) ? 1 : (16 / (int)sizeof(Res));
@@ -146,9 +189,10 @@ __device__ __forceinline__ void run_unit_slice(const WaveParams& wp, const TaskR
                     if constexpr (sizeof(Res) == 1) {
                         pk[v >> 2] |= (uint32_t)(uint8_t)r << ((v & 3) * 8);
                     } else if constexpr (sizeof(Res) == 8) {
-                        unit_acc += (long long)r;
                         unsigned long long bits;
                         memcpy(&bits, &r, 8);
+                        unit_acc += bits & 0xffffffffull;
+                        unit_hi += (unsigned long long)((long long)bits >> 32);
                         pk[2 * v] = (uint32_t)bits;
                         pk[2 * v + 1] = (uint32_t)(bits >> 32);
                     } else {
@@ -174,7 +218,12 @@ __device__ __forceinline__ void run_unit_slice(const WaveParams& wp, const TaskR
                 else a = *reinterpret_cast<const Arg*>(uargs + (size_t)i * wp.arg_stride);
                 const Res r = B::run(a, gidx0 + (i - base), es, rec.attempt);
                 if constexpr (sizeof(Res) == 1) unit_acc32 += (uint32_t)(uint8_t)r;
-                else if constexpr (sizeof(Res) == 8) unit_acc += (long long)r;
+                else if constexpr (sizeof(Res) == 8) {
+                    unsigned long long bits;
+                    memcpy(&bits, &r, 8);
+                    unit_acc += bits & 0xffffffffull;
+                    unit_hi += (unsigned long long)((long long)bits >> 32);
+                }
                 memcpy(dst + (size_t)(i - base) * sizeof(Res), &r, sizeof(Res));
             }
         }
@@ -198,16 +247,16 @@ __global__ void __launch_bounds__(kThreads) dispatch_thread_kernel(const WavePar
     if (threadIdx.x == 0) { s_fault[0] = 0; s_fault[1] = 0; }
     TicketClaimer tc{wp.ticket, 0u};
     tc.prime();
-    long long acc = 0;            // sum of this thread's results over every unit its CTA completed
+    unsigned long long acc = 0, acc_hi = 0;   // sums of this thread's results over every unit its CTA completed
     for (uint32_t iter = 0;; ++iter) {
         const uint32_t t = tc.claim_db(s_ticket, iter);
         if (t >= wp.n_units) break;
         int* const unit_fault = &s_fault[iter & 1];
         const ErrSink es{wp.err_word, unit_fault};
-        const TaskRecord rec = wp.records[t];
-        long long unit_acc = 0;
+        const TaskRecord rec = wave_record(wp, t);
+        unsigned long long unit_acc = 0, unit_hi = 0;
         uint32_t unit_acc32 = 0;
-        run_unit_slice<B, kIndex>(wp, rec, wp.ring + (size_t)t * wp.slot_stride, threadIdx.x, es, unit_acc, unit_acc32);
+        run_unit_slice<B, kIndex>(wp, rec, wp.ring + (size_t)t * wp.slot_stride, threadIdx.x, es, unit_acc, unit_hi, unit_acc32);
         bool lost = false;
         if constexpr (B::kCanFault) {
             __syncthreads();      // every thread's fault reports for this unit are in
@@ -216,17 +265,24 @@ __global__ void __launch_bounds__(kThreads) dispatch_thread_kernel(const WavePar
             // its next writers run after the next claim barrier
             if (threadIdx.x == 0) s_fault[(iter + 1) & 1] = 0;
         }
-        if (!lost) acc += unit_acc + (long long)unit_acc32;   // a lost unit is re-dispatched: never folded twice
+        if (!lost) {                                          // a lost unit is re-dispatched: never folded twice
+            acc += unit_acc + unit_acc32;
+            acc_hi += unit_hi;
+        }
         if (threadIdx.x == 0) {
             // A dead worker loses its whole chunk.  ResilientZPool re-queues it; in the plain ZPool
             // the map would hang forever (fiber/pool.py:801-824 has no try/except) -- here it is
             // reported as a task error instead.
             if (lost && !wp.resilient)
                 atomicMin(wp.err_word, (unsigned long long)(((wp.index_base + rec.first) << 8) | TASK_FAULT));
-            wp.headers[t] = SlotHeader{rec.seq, rec.count | ((lost && wp.resilient) ? kUnitLost : 0u), rec.first};
+            put_header(wp, t, SlotHeader{rec.seq, rec.count | ((lost && wp.resilient) ? kUnitLost : 0u), rec.first});
         }
     }
-    if (wp.sum != nullptr) warp_add(acc, wp.sum);
+    tc.rearm(wp.n_units);
+    if (wp.sum != nullptr) {
+        warp_add(acc, wp.sum);
+        if constexpr (sizeof(typename B::Res) == 8) warp_add(acc_hi, wp.sum_hi);
+    }
 }
 
 // ================================================================================================
@@ -239,11 +295,11 @@ __global__ void __launch_bounds__(kThreads) dispatch_pi_bits_kernel(const WavePa
     __shared__ uint32_t s_ticket[2];
     TicketClaimer tc{wp.ticket, 0u};
     tc.prime();
-    long long acc = 0;
+    unsigned long long acc = 0;
     for (uint32_t iter = 0;; ++iter) {
         const uint32_t t = tc.claim_db(s_ticket, iter);
         if (t >= wp.n_units) break;
-        const TaskRecord rec = wp.records[t];
+        const TaskRecord rec = wave_record(wp, t);
         uint8_t* slot = wp.ring + (size_t)t * wp.slot_stride;
         for (uint32_t b = threadIdx.x * 2; b < rec.count; b += kThreads * 2) {
             const int64_t a0 = wp.index_start + (int64_t)((rec.first + b) * 8ull) * wp.index_step;
@@ -256,8 +312,65 @@ __global__ void __launch_bounds__(kThreads) dispatch_pi_bits_kernel(const WavePa
                 acc += __popc(bits & 0xffu);
             }
         }
-        if (threadIdx.x == 0) wp.headers[t] = SlotHeader{rec.seq, rec.count, rec.first};
+        if (threadIdx.x == 0) put_header(wp, t, SlotHeader{rec.seq, rec.count, rec.first});
     }
+    tc.rearm(wp.n_units);
+    if (wp.sum != nullptr) warp_add(acc, wp.sum);
+}
+
+// ================================================================================================
+// dispatch: bit-packed twin of a bool ThreadBody with EXPLICIT argument items (B::Arg records, 8 per
+// byte-task).  A warp takes 512 consecutive items per pass: lane l evaluates items l, l+32, ... (each
+// load instruction reads 32 consecutive records: fully coalesced), and the ballot of pass j IS word j
+// of the warp's 64 output bytes (bit l = lane l's result = item 32j + l) -- no shuffles, no transposes.
+// Lanes 0..15 store the 16 words: 64 contiguous bytes per warp.  Items at or past wp.n_items are not
+// read and leave zero bits.  Algorithmic bytes per item: sizeof(Arg) read + 1/8 written.
+// ================================================================================================
+template <class B>
+__global__ void __launch_bounds__(kThreads) dispatch_bits_items_kernel(const WaveParams wp) {
+    using Arg = typename B::Arg;
+    static_assert(!B::kCanFault, "bit-packed twins are for bodies that cannot lose a unit");
+    __shared__ uint32_t s_ticket[2];
+    __shared__ int s_fault;
+    TicketClaimer tc{wp.ticket, 0u};
+    tc.prime();
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const ErrSink es{wp.err_word, &s_fault};
+    unsigned long long acc = 0;
+    for (uint32_t iter = 0;; ++iter) {
+        const uint32_t t = tc.claim_db(s_ticket, iter);
+        if (t >= wp.n_units) break;
+        const TaskRecord rec = wave_record(wp, t);
+        uint8_t* slot = wp.ring + (size_t)t * wp.slot_stride;
+        const uint8_t* uargs = wp.args + rec.arg_off;
+        const uint64_t item0 = rec.first * 8ull;                       // map-level index of the unit's first item
+        const uint32_t n_it = rec.count * 8u;                          // items covered by this unit's bytes
+        for (uint32_t base = warp * 512u; base < n_it; base += (kThreads / 32) * 512u) {
+            uint32_t mine = 0u;                                        // word `lane` of this pass block (lanes 0..15)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const uint32_t i = base + 32u * j + lane;
+                bool r = false;
+                if (i < n_it && item0 + i < wp.n_items) {
+                    const Arg a = *reinterpret_cast<const Arg*>(uargs + (size_t)i * sizeof(Arg));
+                    r = B::run(a, wp.index_base + item0 + i, es, rec.attempt) != 0;
+                }
+                const uint32_t word = __ballot_sync(0xffffffffu, r);
+                if (lane == (uint32_t)j) mine = word;
+            }
+            if (lane < 16) {
+                const uint32_t byte0 = (base >> 3) + lane * 4u;            // this word's first byte inside the slot
+                if (byte0 + 4u <= rec.count) {
+                    *reinterpret_cast<uint32_t*>(slot + byte0) = mine;
+                } else {
+                    for (uint32_t b = byte0; b < rec.count; ++b) slot[b] = (uint8_t)(mine >> ((b - byte0) * 8u));
+                }
+                acc += __popc(mine);
+            }
+        }
+        if (threadIdx.x == 0) put_header(wp, t, SlotHeader{rec.seq, rec.count, rec.first});
+    }
+    tc.rearm(wp.n_units);
     if (wp.sum != nullptr) warp_add(acc, wp.sum);
 }
 
@@ -275,7 +388,7 @@ __global__ void __launch_bounds__(kThreads) dispatch_payload_map_kernel(const Wa
     for (;;) {
         const uint32_t t = tc.claim(&s_ticket);
         if (t >= wp.n_units) break;
-        const TaskRecord rec = wp.records[t];
+        const TaskRecord rec = wave_record(wp, t);
         const uint8_t* src = wp.args + rec.arg_off + threadIdx.x * 16;
         uint8_t* dst = wp.ring + (size_t)t * wp.slot_stride + threadIdx.x * 16;
         const uint32_t tbase = (uint32_t)(wp.index_base + rec.first);
@@ -301,8 +414,9 @@ __global__ void __launch_bounds__(kThreads) dispatch_payload_map_kernel(const Wa
             v.z = v.z * kPayloadMul + tt; v.w = v.w * kPayloadMul + tt;
             st_vec(dst + (size_t)r * kPayloadBytes, v);
         }
-        if (threadIdx.x == 0) wp.headers[t] = SlotHeader{rec.seq, rec.count, rec.first};
+        if (threadIdx.x == 0) put_header(wp, t, SlotHeader{rec.seq, rec.count, rec.first});
     }
+    tc.rearm(wp.n_units);
 }
 
 // ================================================================================================
@@ -314,11 +428,11 @@ __global__ void __launch_bounds__(kThreads) dispatch_payload_checksum_kernel(con
     TicketClaimer tc{wp.ticket, 0u};
     tc.prime();
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    long long acc = 0;
+    unsigned long long acc = 0;
     for (;;) {
         const uint32_t t = tc.claim(&s_ticket);
         if (t >= wp.n_units) break;
-        const TaskRecord rec = wp.records[t];
+        const TaskRecord rec = wave_record(wp, t);
         uint32_t* dst = reinterpret_cast<uint32_t*>(wp.ring + (size_t)t * wp.slot_stride);
         for (uint32_t r = warp; r < rec.count; r += kThreads / 32) {
             const uint8_t* src = wp.args + rec.arg_off + (size_t)r * wp.arg_stride + lane * 16;
@@ -330,10 +444,11 @@ __global__ void __launch_bounds__(kThreads) dispatch_payload_checksum_kernel(con
             for (int k = 0; k < 8; ++k) s += v[k].x + v[k].y + v[k].z + v[k].w;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0) { dst[r] = s; acc += (long long)s; }
+            if (lane == 0) { dst[r] = s; acc += s; }
         }
-        if (threadIdx.x == 0) wp.headers[t] = SlotHeader{rec.seq, rec.count, rec.first};
+        if (threadIdx.x == 0) put_header(wp, t, SlotHeader{rec.seq, rec.count, rec.first});
     }
+    tc.rearm(wp.n_units);
     if (wp.sum != nullptr) warp_add(acc, wp.sum);
 }
 
@@ -354,7 +469,7 @@ __global__ void __launch_bounds__(kThreads) dispatch_parzen_kernel(const WavePar
     for (;;) {
         const uint32_t t = tc.claim(&s_ticket);
         if (t >= wp.n_units) break;
-        const TaskRecord rec = wp.records[t];
+        const TaskRecord rec = wave_record(wp, t);
         double* dst = reinterpret_cast<double*>(wp.ring + (size_t)t * wp.slot_stride);
         for (uint32_t i = 0; i < rec.count; ++i) {
             const double h = *reinterpret_cast<const double*>(wp.args + rec.arg_off + (size_t)i * wp.arg_stride);
@@ -391,8 +506,9 @@ __global__ void __launch_bounds__(kThreads) dispatch_parzen_kernel(const WavePar
             }
             __syncthreads();
         }
-        if (threadIdx.x == 0) wp.headers[t] = SlotHeader{rec.seq, rec.count, rec.first};
+        if (threadIdx.x == 0) put_header(wp, t, SlotHeader{rec.seq, rec.count, rec.first});
     }
+    tc.rearm(wp.n_units);
 }
 
 // ================================================================================================
@@ -711,9 +827,13 @@ __global__ void __launch_bounds__(160) dispatch_payload_map_tma_kernel(const Wav
         };
         for (;;) {
             const uint32_t t = atomicAdd(wp.ticket, 1u);
-            if (t >= wp.n_units) break;
-            const TaskRecord rec = wp.records[t];
-            wp.headers[t] = SlotHeader{rec.seq, rec.count, rec.first};
+            if (t >= wp.n_units) {
+                // no prefetch here: each CTA draws exactly one ticket >= n_units; the highest re-arms the counter
+                if (t == wp.n_units + gridDim.x - 1u) *wp.ticket = 0u;
+                break;
+            }
+            const TaskRecord rec = wave_record(wp, t);
+            put_header(wp, t, SlotHeader{rec.seq, rec.count, rec.first});
             const uint8_t* src = wp.args + rec.arg_off;
             uint8_t* dst = wp.ring + (size_t)t * wp.slot_stride;
             const uint32_t total = rec.count * kPayloadBytes;

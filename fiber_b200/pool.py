@@ -54,13 +54,19 @@ class _Engine:
 
 
 class _Segment:
-    """Pinned result segment of one map: exposes ``__array_interface__`` so NumPy views keep it (and
-    through it the engine) alive; releasing it returns the segment to the pool's pinned ring
-    (``self._inventory[job_seq] = None``, fiber/pool.py:677-679)."""
+    """Owner of one map's engine state (its seq: control slots, events, pinned result segment) from the
+    moment it is submitted.  Once the map has finished, ``bind`` exposes the pinned segment through
+    ``__array_interface__`` so NumPy views keep it (and through it the engine) alive.  Dropping the last
+    reference -- a fetched result going away, but also a fire-and-forget ``map_async`` or an abandoned
+    ``imap`` generator -- releases the seq (``self._inventory[job_seq] = None``, fiber/pool.py:677-679)."""
 
-    def __init__(self, engine, seq, ptr, nbytes):
-        self.engine, self.seq, self.ptr, self.nbytes = engine, seq, ptr, nbytes
+    def __init__(self, engine, seq):
+        self.engine, self.seq, self.ptr, self.nbytes = engine, seq, None, 0
+
+    def bind(self, ptr, nbytes):
+        self.ptr, self.nbytes = ptr, nbytes
         self.__array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr or 0, False), "version": 3}
+        return self
 
     def __del__(self):
         eng = getattr(self, "engine", None)
@@ -192,6 +198,11 @@ class ResultArray(collections.abc.Sequence):
             return self._sum
         if self._bits is not None:
             return int(np.unpackbits(self._bits).sum())   # the bits past n are zero
+        if self._a.dtype.kind in "iu" and self._a.dtype.itemsize == 8:
+            # int64 results: NumPy's sum wraps silently, Python's sum of the reference's list does not
+            lo = int((self._a.view(np.uint64) & np.uint64(0xFFFFFFFF)).sum(dtype=np.uint64))
+            hi = int((self._a.view(np.int64) >> np.int64(32)).sum(dtype=np.int64))
+            return hi * (1 << 32) + lo
         return int(self._a.sum())
 
     def sort(self):
@@ -205,7 +216,8 @@ class MapResult:
         self._pool, self._engine, self._spec, self._seq, self._n = pool, engine, spec, seq, n
         self._keepalive = keepalive   # argument buffers must outlive the asynchronous H2D copies
         self._result = None
-        self._segment = None
+        self._exc = None              # a task error is raised again by every later get()
+        self._segment = _Segment(engine, seq) if n else None   # owns the seq from submission on
         self._yielded = False
         self._n_items = None          # bit-packed maps: number of range() indices (n = ceil(n_items / 8) byte tasks)
         self._user_spec = spec
@@ -214,6 +226,8 @@ class MapResult:
     def _wait(self, timeout=None):
         if self._result is not None:
             return self._result
+        if self._exc is not None:
+            raise self._exc
         if self._n == 0:
             us = self._user_spec
             self._result = ResultArray(us, np.empty((0,) + us.result_dtype()[1], us.result_dtype()[0]), 0)
@@ -225,16 +239,20 @@ class MapResult:
         if rc == _abi.FBR_ETIMEOUT:
             raise TimeoutError("map %d not finished" % self._seq)
         if rc == _abi.FBR_ETASK:
-            self._segment = _Segment(eng, self._seq, res.data, 0)  # release on GC
-            self._raise_task_error(res)
+            try:
+                self._raise_task_error(res)
+            except Exception as e:      # noqa: BLE001 -- remembered: later get() calls raise it without touching the engine
+                self._exc = e
+                raise
         _abi.check(rc)
         self._keepalive = None
         self._pool.recv_tasks += self._n if self._n_items is None else self._n_items
         dtype, sub = self._spec.result_dtype()
-        dsum = int(res.sum) if (self._flags & _abi.FBR_WANT_SUM) else None
+        # exact, unbounded sum: the device folds the two halves of int64 results separately (nothing wraps)
+        dsum = (int(res.sum_hi) * (1 << 32) + int(res.sum_lo)) if (self._flags & _abi.FBR_WANT_SUM) else None
         self.n_waves = res.n_waves
         if self._flags & _abi.FBR_RESULTS_ON_DEVICE:
-            seg = _Segment(eng, self._seq, None, 0)          # owns the seq (device buffer) until GC
+            seg = self._segment                              # owns the seq (device buffer) until GC
             rb, seq = res.result_bytes, self._seq
 
             def fetch(lo, hi, seg=seg):
@@ -242,12 +260,10 @@ class MapResult:
                 if hi > lo:
                     _abi.check(eng.lib.fbr_result_fetch(eng.handle, seq, lo, hi - lo, ctypes.c_void_p(block.ptr)))
                 return np.asarray(block)[: (hi - lo) * rb].view(dtype).reshape((hi - lo,) + sub)
-            self._segment = seg
             self._result = ResultArray(self._spec, None, dsum, n=int(res.n_tasks), fetch=fetch)
             return self._result
-        seg = _Segment(eng, self._seq, res.data, res.n_tasks * res.result_bytes)
+        seg = self._segment.bind(res.data, res.n_tasks * res.result_bytes)
         arr = np.asarray(seg).view(dtype).reshape((res.n_tasks,) + sub)
-        self._segment = seg
         if self._n_items is not None:
             # bit-packed map (pi_inside_bits8): `arr` holds ceil(n/8) bytes.  The body evaluated all 8
             # indices of the last byte; the ones past the end of the range are dropped here, from the
@@ -372,6 +388,12 @@ class ExpressResult:
         self._pool, self._x, self._spec, self._ticket = pool, express, spec, ticket
         self._done, self._value, self._exc = False, None, None
 
+    def __del__(self):
+        # handle dropped without a get(): tell the lane to forget the response instead of parking it forever
+        x = getattr(self, "_x", None)
+        if x is not None and not getattr(self, "_done", True) and x.handle:
+            x.lib.fbr_express_discard(x.handle, self._ticket)
+
     def get(self, timeout=None):
         if self._done:
             if self._exc is not None:
@@ -407,21 +429,29 @@ class Pool:
         self._processes = processes if processes is not None else 1   # fiber/pool.py:894
         if self._processes < 1:
             raise ValueError("Number of processes must be at least 1")
-        if initializer is not None:
+        if initializer is not None and getattr(initializer, "__fbr_init_body__", None) is None:
             # the reference runs initializer(*initargs) inside every worker process
-            # (fiber/pool.py:858-859); a host callable cannot run inside a GPU worker.
-            raise NotImplementedError("fiber_b200.Pool: Python initializers cannot run on GPU workers")
+            # (fiber/pool.py:858-859); a host callable cannot run inside a GPU worker.  What the idiom is
+            # for -- giving every task the same large arguments once -- is the engine's broadcast block:
+            # see fiber_b200.device_initializer.
+            raise NotImplementedError("fiber_b200.Pool: Python initializers cannot run on GPU workers; bind the "
+                                      "initializer with @fiber_b200.device_initializer(body) to upload initargs as "
+                                      "the body's broadcast block")
         self._initializer, self._initargs = initializer, initargs
+        self._init_block = None   # (body name, blob, handle): initargs uploaded once per worker at start
         self._maxtasksperchild = maxtasksperchild
         self._error_handling = bool(error_handling)
         self._devices = list(devices) if devices is not None else None
         self._ring_bytes = int(ring_bytes)
         self._timing = bool(timing)
-        if results not in ("host", "device", "bits"):
-            raise ValueError("results must be 'host' (pinned result segment), 'device' (stay in HBM, fetched lazily) "
-                             "or 'bits' (bool results of range() maps packed 8 to a byte end to end)")
+        if results not in ("host", "bytes", "device", "bits"):
+            raise ValueError("results must be 'host' (pinned result segment; bool results packed one bit each), "
+                             "'bytes' (pinned result segment, one byte per bool), 'device' (stay in HBM, fetched "
+                             "lazily) or 'bits' (same as 'host')")
         self._results_on_device = results == "device"
-        self._results_bits = results == "bits"
+        # A bool needs one bit: bool bodies with a bit-packed twin run through it by default, so the ring, the
+        # ordered output and the D2H copy move n/8 bytes.  ResultArray hides the layout; 'bytes' opts out.
+        self._results_bits = results in ("host", "bits")
         self._use_express = bool(express) and not self._error_handling
         self._express_idle_us = int(express_idle_us)
         self._express = None
@@ -455,6 +485,11 @@ class Pool:
                 from .affinity import bind_to_device
                 self.bound_cpus = bind_to_device(devs[0])
             self._engine = _Engine(len(devs), devs, self._ring_bytes, self._timing)
+            if self._initializer is not None:
+                # initializer(*initargs) in every worker (fiber/pool.py:858-859) == one broadcast block per device
+                body = self._initializer.__fbr_init_body__
+                blob = registry.spec(body).shared_block(*self._initargs)
+                self._init_block = (body, blob, self._shared_handle(blob))
         self._worker_handler_started = True
 
     def lazy_start_workers(self, func):
@@ -529,6 +564,15 @@ class Pool:
             d.shared = self._shared_handle(enc.shared)
             d.shared_bytes = len(enc.shared)
             flags |= _abi.FBR_SHARED_HANDLE
+        elif spec.flags & _abi.FBR_BODY_NEEDS_SHARED:
+            # tasks without their own shared arguments read the block the pool's initializer uploaded
+            if self._init_block is None or self._init_block[0] != spec.name:
+                raise TypeError("%s: tasks carry no shared arguments and the pool has no initializer block for this "
+                                "body (Pool(initializer=<@device_initializer(%r)>, initargs=...))" % (spec.name, spec.name))
+            d.shared = self._shared_handle(self._init_block[1])
+            d.shared_bytes = len(self._init_block[1])
+            flags |= _abi.FBR_SHARED_HANDLE
+        d.n_items = enc.n_items
         d.task_index_base = enc.task_index_base
         d.flags = flags
         seq = ctypes.c_uint64(0)
@@ -560,15 +604,20 @@ class Pool:
             iterable = list(iterable)
         spec = self._spec_of(func)
         self.lazy_start_workers(func)
-        if self._results_bits and isinstance(iterable, range) and spec.name in registry.BITS_TWIN:
-            # a bool needs one bit: the twin body computes 8 consecutive indices per result byte, so the
-            # ring, the gather and the D2H copy move n/8 bytes instead of n
-            twin = registry.spec(registry.BITS_TWIN[spec.name])
-            r = self._submit(func, twin.encode_range(iterable), _abi.FBR_MAP, max(1, chunksize // 8), spec=twin)
-            r._n_items, r._user_spec = len(iterable), spec
-            self.sent_tasks += len(iterable) - r._n
-            return r
-        return self._submit(func, spec.encode_map(iterable), _abi.FBR_MAP, chunksize)
+        enc = spec.encode_map(iterable)
+        if self._results_bits and spec.name in registry.BITS_TWIN:
+            return self._submit_bits(func, spec, enc, _abi.FBR_MAP, chunksize)
+        return self._submit(func, enc, _abi.FBR_MAP, chunksize)
+
+    def _submit_bits(self, func, spec, enc, kind, chunksize):
+        """A bool needs one bit: the twin body evaluates 8 consecutive items (range() indices or argument
+        records) per result byte, so the ring, the ordered output and the D2H copy move n/8 bytes."""
+        twin = registry.spec(registry.BITS_TWIN[spec.name])
+        n_items = enc.n
+        r = self._submit(func, twin.from_encoded(enc), kind, max(1, chunksize // 8), spec=twin)
+        r._n_items, r._user_spec = n_items, spec
+        self.sent_tasks += n_items - r._n
+        return r
 
     def map(self, func, iterable, chunksize=None):
         return self.map_async(func, iterable, chunksize).get()
@@ -581,7 +630,10 @@ class Pool:
             iterable = list(iterable)
         spec = self._spec_of(func)
         self.lazy_start_workers(func)
-        return self._submit(func, spec.encode_starmap(iterable), _abi.FBR_STARMAP, chunksize)
+        enc = spec.encode_starmap(iterable)
+        if self._results_bits and spec.name in registry.BITS_TWIN:
+            return self._submit_bits(func, spec, enc, _abi.FBR_STARMAP, chunksize)
+        return self._submit(func, enc, _abi.FBR_STARMAP, chunksize)
 
     def starmap(self, func, iterable, chunksize=None):
         return self.starmap_async(func, iterable, chunksize).get()

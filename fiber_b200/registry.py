@@ -21,17 +21,63 @@ from . import _abi
 _BOUND = {}  # callables that cannot carry attributes (builtins) -> body name
 
 
-def device_body(name, **meta):
-    """Decorator: ``@device_body("pi_inside_det")`` binds ``func`` to the compiled-in device body
-    ``name`` and sets ``func.__fiber_meta__`` (``gpu=1`` unless overridden), like ``fiber.meta``."""
-    from .meta import post_process, VALID_META_KEYS
+def device_body(name, source=None, entry="fbr_body_entry", args="i64", **meta):
+    """Decorator: ``@device_body("pi_inside_det")`` binds ``func`` to the device body ``name`` and sets
+    ``func.__fiber_meta__`` (``gpu=1`` unless overridden), like ``fiber.meta``.
+
+    ``source=`` makes it an OUT-OF-TREE body: CUDA source of a translation unit that includes
+    ``fiber_b200_body.cuh``, defines a ThreadBody and exports it with
+    ``FBR_EXPORT_THREAD_BODY(Body, "<name>", <entry>, kind, flags)``.  It is compiled for sm_100a with
+    nvcc (cached by content hash under ``fiber_b200/_lib/bodies/``) and registered with
+    ``fbr_register_body`` -- the reference ships any callable to its workers (fiber/pool.py:961); this is
+    how a callable that is not compiled into libfiber_b200 gets its device code there.  ``args`` names the
+    argument record layout: ``"i64"`` (one int) or ``"i64x2"`` (two ints)."""
+    from .meta import VALID_META_KEYS
     for k in meta:
         assert k in VALID_META_KEYS, "Invalid meta argument \"{}\"".format(k)
     md = {"gpu": 1}
     md.update(meta)
+    if source is not None:
+        from . import bodies
+        register_module(name, bodies.compile_module(name, source), entry, args)
 
     def decorator(func):
         bind(func, name, **md)
+        return func
+    return decorator
+
+
+def register_module(name, module_path, entry="fbr_body_entry", args="i64"):
+    """``fbr_register_body`` + the host-side encoder for the body's argument records."""
+    import ctypes
+    L = _abi.load()
+    fid = ctypes.c_int(-1)
+    _abi.check(L.fbr_register_body(name.encode(), str(module_path).encode(), entry.encode(), ctypes.byref(fid)))
+    specs = _load_specs()
+    if name not in specs:
+        info = _abi.BodyInfo()
+        _abi.check(L.fbr_body_info(fid.value, ctypes.byref(info)))
+        if args == "i64":
+            specs[name] = _UnaryI64(info)
+        elif args == "i64x2":
+            specs[name] = _BinaryI64(info)
+        else:
+            raise ValueError("unknown argument layout %r (have: i64, i64x2)" % (args,))
+    return specs[name]
+
+
+def device_initializer(body_name):
+    """Bind a pool ``initializer`` to the broadcast block of device body ``body_name``.
+
+    The reference runs ``initializer(*initargs)`` once in every worker process (fiber/pool.py:858-859),
+    the idiom for giving all tasks the same large arguments without pickling them per task.  A host
+    callable cannot run inside a GPU worker; what the idiom *means* maps exactly onto the engine's
+    broadcast blocks: ``Pool(initializer=f, initargs=(...))`` with ``f`` decorated here uploads
+    ``spec(body_name).shared_block(*initargs)`` once to every worker (``fbr_shared_put``), and tasks of that
+    body submitted without their own shared arguments read it."""
+    def decorator(func):
+        spec(body_name)
+        func.__fbr_init_body__ = body_name
         return func
     return decorator
 
@@ -67,12 +113,13 @@ def body_name_of(func):
 # ------------------------------------------------------------------------------------------------
 class Encoded:
     """Fixed-layout form of one map's arguments."""
-    __slots__ = ("n", "args", "arg_stride", "index_start", "index_step", "shared", "task_index_base", "keepalive")
+    __slots__ = ("n", "args", "arg_stride", "index_start", "index_step", "shared", "task_index_base", "keepalive", "n_items")
 
-    def __init__(self, n, args=None, arg_stride=0, index_start=0, index_step=1, shared=None, task_index_base=0):
+    def __init__(self, n, args=None, arg_stride=0, index_start=0, index_step=1, shared=None, task_index_base=0, n_items=0):
         self.n, self.args, self.arg_stride = n, args, arg_stride
         self.index_start, self.index_step = index_start, index_step
         self.shared, self.task_index_base = shared, task_index_base
+        self.n_items = n_items     # bit-packed twins: argument items of the whole map (8 per task, the last may be short)
 
 
 def _as_i64(values, what):
@@ -225,9 +272,16 @@ class _UnaryI64(BodySpec):
 
 
 class _Bits8(BodySpec):
-    """``pi_inside_bits8``: task g = the 8 range() indices 8g..8g+7, result = one byte (bit k = index
-    8g+k).  Not bound to a callable: ``Pool(results="bits")`` routes ``map(is_inside, range(n))`` here
+    """``pi_inside_bits8``: task g = items 8g..8g+7 (range() indices or int64 arguments), result = one byte
+    (bit k = item 8g+k).  Not bound to a callable: ``Pool`` routes maps of the bool body here
     (``BITS_TWIN``) and presents the bytes as a bit-backed ``ResultArray``."""
+
+    def from_encoded(self, enc):
+        """Re-express the bool body's encoded map (one int64 record or range() index per task) as byte-tasks."""
+        n = enc.n
+        if enc.arg_stride == 0:
+            return Encoded((n + 7) // 8, index_start=enc.index_start, index_step=enc.index_step, n_items=n)
+        return Encoded((n + 7) // 8, args=enc.args, arg_stride=64, n_items=n)
 
     def result_dtype(self):
         return np.dtype(np.uint8), ()
@@ -239,7 +293,7 @@ class _Bits8(BodySpec):
         if len(items) and not (-2 ** 63 <= items[0] <= 2 ** 63 - 1 and -2 ** 63 <= items[-1] + 7 * items.step <= 2 ** 63 - 1
                                and -2 ** 63 <= items[-1] <= 2 ** 63 - 1):
             raise OverflowError("range() bounds exceed the int64 task record")
-        return Encoded((len(items) + 7) // 8, index_start=items.start, index_step=items.step)
+        return Encoded((len(items) + 7) // 8, index_start=items.start, index_step=items.step, n_items=len(items))
 
 
 # bool bodies that have a bit-packed twin: 8 consecutive range() indices per result byte
@@ -328,10 +382,23 @@ class _Parzen(BodySpec):
         body = np.ascontiguousarray(xs, dtype=self.elem)  # the one cast to fp32 for parzen_f32
         return hdr.tobytes() + body.tobytes()
 
+    def _fast_map_ok(self, items):
+        # map(func, widths): the samples come from the pool's broadcast block (Pool(initializer=, initargs=))
+        return True
+
     def _encode(self, items, fast, apply=False):
+        if fast:
+            return Encoded(len(items), args=np.ascontiguousarray(list(items), dtype=np.float64), arg_stride=8)
         hs, first = [], None
         for it in items:
             args, kwds = self._split(it, apply)
+            if len(args) == 1 and not kwds:        # (h,): samples from the broadcast block
+                if first is not None:
+                    raise TypeError("parzen_estimation: mixed (h,) and (x_samples, point_x, h) items in one map")
+                hs.append(float(args[0]))
+                continue
+            if hs and first is None:
+                raise TypeError("parzen_estimation: mixed (h,) and (x_samples, point_x, h) items in one map")
             vals = dict(zip(("x_samples", "point_x", "h"), args))
             vals.update(kwds)
             if set(vals) != {"x_samples", "point_x", "h"}:
@@ -397,7 +464,7 @@ def _load_specs():
         info = _abi.BodyInfo()
         _abi.check(L.fbr_body_info(fid, ctypes.byref(info)))
         name = info.name.decode()
-        if name in ("square_i64", "identity_i64", "pi_inside_det", "fault_identity_i64"):
+        if name in ("square_i64", "identity_i64", "pi_inside_det", "fault_identity_i64", "trap_identity_i64"):
             s = _UnaryI64(info)
         elif name == "mul2_i64":
             s = _BinaryI64(info)

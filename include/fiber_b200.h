@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FBR_ABI_VERSION 1
+#define FBR_ABI_VERSION 2
 
 typedef enum fbr_status {
     FBR_OK = 0,
@@ -55,10 +55,12 @@ typedef enum fbr_result_kind {
     FBR_RES_U32 = 3,     /* uint32     (Python int) */
     FBR_RES_F64X2 = 4,   /* two float64 (Python tuple of floats) */
     FBR_RES_NONE = 5,    /* body returns None; one pad byte per task */
-    FBR_RES_BITS8 = 6    /* one byte = the bool results of 8 consecutive range() indices, bit k (LSB first)
-                            = index 8*task + k.  A map over N indices is submitted as ceil(N/8) tasks;
-                            the bits past N in the last byte are computed like any other index and are
-                            masked by the caller (fiber_b200/pool.py does) */
+    FBR_RES_BITS8 = 6    /* one byte = the bool results of 8 consecutive items, bit k (LSB first) = item
+                            8*task + k.  A map over N items is submitted as ceil(N/8) tasks: range() indices
+                            (arg_stride 0) or 8 argument items per task record (arg_stride = 8 * item size,
+                            fbr_map_desc_t.n_items = N so that items past N are never read).  For range()
+                            indices the bits past N in the last byte are computed like any other index and
+                            are masked by the caller (fiber_b200/pool.py does) */
 } fbr_result_kind;
 
 #define FBR_BODY_INDEX_ARG 0x1u   /* body can take the task index itself as its int64 argument */
@@ -79,6 +81,27 @@ typedef struct fbr_body_info {
 int fbr_body_count(int* n);
 int fbr_body_info(int func_id, fbr_body_info_t* info);
 int fbr_body_lookup(const char* name, int* func_id);
+
+/* Out-of-tree device bodies.  The reference pickles ANY callable into the task tuple
+ * (fiber/pool.py:961) and the worker calls it (fiber/pool.py:806,809,820); here the callable's device
+ * code may be compiled separately from this library: a shared object built with nvcc for sm_100a from a
+ * source that includes include/fiber_b200_body.cuh, defines a ThreadBody struct and exports it with
+ * FBR_EXPORT_THREAD_BODY(Body, name, entry).  fbr_register_body dlopen()s `module_path`, calls `entry`
+ * to obtain the module descriptor below, checks its ABI stamp and appends the body to the table
+ * (func_id >= the compiled-in count; the same name may be registered once).  The module's launch routine
+ * receives the same wave parameters as the compiled-in kernels, so registered bodies run in the same
+ * persistent-CTA dispatch kernels (direct placement, ring + gather_ordered, resilient re-dispatch). */
+#define FBR_BODY_MODULE_ABI 1
+typedef struct fbr_body_module {
+    uint32_t abi;               /* FBR_BODY_MODULE_ABI */
+    uint32_t wave_params_bytes; /* sizeof(fbr::WaveParams) the module was compiled against */
+    const char* name;
+    uint32_t arg_bytes, result_bytes, result_kind, flags, unit_tasks;
+    void (*launch)(const void* wave_params, int grid, void* cuda_stream);
+    int (*occupancy)(int index_mode);   /* resident CTAs per SM on the current device */
+} fbr_body_module_t;
+typedef const fbr_body_module_t* (*fbr_body_entry_fn)(void);
+int fbr_register_body(const char* name, const char* module_path, const char* entry, int* func_id);
 
 /* ---- pool lifecycle -------------------------------------------------------------------------
  * fbr_pool_create   <- ZPool.__init__ (fiber/pool.py:888-943) + worker start
@@ -127,6 +150,9 @@ int fbr_pool_worker_device(fbr_pool_t* pool, int worker, int* device_id);
 #define FBR_RESULTS_ON_DEVICE 0x800u /* keep the ordered results in an engine-owned device buffer (per
                                    worker block); nothing but the 24-byte control block crosses PCIe
                                    until fbr_result_fetch asks for a range */
+#define FBR_VIA_RING 0x1000u    /* always go through task records + result ring + gather_ordered, even for a
+                                   contiguous block whose units could be stored at their final index by
+                                   the dispatch kernel (direct placement) */
 #define FBR_RESILIENT 0x400u    /* ResilientZPool semantics (fiber/pool.py:1425-1688): a claim unit whose
                                    worker dies (FBR_TASK_FAULT) is re-dispatched until it completes */
 
@@ -144,6 +170,8 @@ typedef struct fbr_map_desc {
     void* out;               /* NULL: engine-owned pinned result segment; else n_tasks*result_bytes */
     uint64_t task_index_base;/* global index of task 0 (sharded maps: rank's block start) */
     uint64_t shuffle_seed;
+    uint64_t n_items;        /* FBR_RES_BITS8 bodies with explicit arguments: number of argument items of the
+                                whole map (the last task may cover fewer than 8); 0 = 8 * n_tasks */
 } fbr_map_desc_t;
 
 int fbr_map_submit(fbr_pool_t* pool, const fbr_map_desc_t* desc, uint64_t* seq);
@@ -178,10 +206,14 @@ typedef struct fbr_result {
     uint32_t result_bytes;
     uint32_t result_kind;
     void* data;              /* ordered results: pinned host (or the caller's `out`) */
-    int64_t sum;             /* valid with FBR_WANT_SUM */
+    int64_t sum;             /* valid with FBR_WANT_SUM: sum(results), wrapped to int64 */
     uint32_t err_code;       /* 0, or fbr_task_error of the lowest failing task */
     uint32_t n_waves;
     uint64_t err_task;       /* index of that task */
+    uint64_t sum_lo;         /* the exact sum is sum_hi * 2^32 + sum_lo (Python ints are unbounded: the device */
+    int64_t sum_hi;          /* folds the two halves of int64 results separately, so nothing wraps silently) */
+    uint32_t sum_overflow;   /* 1: the exact sum does not fit int64, `sum` is its low 64 bits */
+    uint32_t pad;
 } fbr_result_t;
 
 typedef enum fbr_task_error {
@@ -222,6 +254,9 @@ typedef struct fbr_stats {
     uint64_t gather_bytes;              /* algorithmic bytes moved by gather_ordered (read+write) */
     uint64_t dispatch_bytes;            /* algorithmic bytes of the dispatch kernels (args+results) */
     uint64_t units_redispatched;        /* lost units re-queued by resilient maps (pending-table resubmits) */
+    uint64_t records_copied;            /* task records written to the pinned ring and copied to the device */
+    uint64_t direct_waves;              /* waves whose dispatch kernel stored at the final index (no gather) */
+    uint64_t workers_respawned;         /* workers whose CUDA context died and was rebuilt (resilient pools) */
 } fbr_stats_t;
 int fbr_pool_stats(fbr_pool_t* pool, fbr_stats_t* stats);
 int fbr_pool_stats_reset(fbr_pool_t* pool);
@@ -283,6 +318,7 @@ const char* fbr_express_last_error(void);
 int fbr_express_create(int device_id, int idle_timeout_us, fbr_express_t** x);
 int fbr_express_submit(fbr_express_t* x, int func_id, const void* arg, uint32_t arg_bytes, uint64_t* ticket);
 int fbr_express_wait(fbr_express_t* x, uint64_t ticket, void* result, uint32_t* result_bytes, uint32_t* err, int timeout_ms);
+int fbr_express_discard(fbr_express_t* x, uint64_t ticket);   /* handle dropped without a wait: forget the response */
 int fbr_express_stats(fbr_express_t* x, uint64_t* served, uint64_t* launches, int* resident);
 int fbr_express_destroy(fbr_express_t* x);
 

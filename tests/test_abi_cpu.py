@@ -41,7 +41,7 @@ def test_header_constants_match_binding():
         m = re.search(r"%s = (-\d+)" % name, header)
         assert m and int(m.group(1)) == getattr(_abi, name), name
     # struct sizes the C side static_asserts / the binding mirrors
-    assert ctypes.sizeof(_abi.MapDesc) == 88 and ctypes.sizeof(_abi.Result) == 56 and ctypes.sizeof(_abi.BodyInfo) == 64
+    assert ctypes.sizeof(_abi.MapDesc) == 96 and ctypes.sizeof(_abi.Result) == 80 and ctypes.sizeof(_abi.Stats) == 128 and ctypes.sizeof(_abi.BodyInfo) == 64
 
 
 def test_body_table():
@@ -257,10 +257,18 @@ def test_bits_body_and_bit_backed_result_array():
     from fiber_b200.pool import ResultArray
     s = registry.spec("pi_inside_bits8")
     assert (s.result_bytes, s.result_kind) == (1, _abi.FBR_RES_BITS8)
-    assert s.flags & _abi.FBR_BODY_INDEX_ONLY and s.flags & _abi.FBR_BODY_SUMMABLE
+    assert s.flags & _abi.FBR_BODY_INDEX_ARG and s.flags & _abi.FBR_BODY_SUMMABLE and s.arg_bytes == 64
     assert registry.BITS_TWIN["pi_inside_det"] == "pi_inside_bits8"
     e = s.encode_range(range(3, 1003, 5))
-    assert (e.n, e.arg_stride, e.index_start, e.index_step) == (25, 0, 3, 5)
+    assert (e.n, e.arg_stride, e.index_start, e.index_step, e.n_items) == (25, 0, 3, 5, 200)
+    # explicit arguments: 8 int64 items per byte-task, the map's item count travels in n_items
+    base = registry.spec("pi_inside_det")
+    e = s.from_encoded(base.encode_map([5, 6, 7, 8, 9, 10, 11, 12, 13]))
+    assert (e.n, e.arg_stride, e.n_items) == (2, 64, 9) and e.args.tolist() == list(range(5, 14))
+    e = s.from_encoded(base.encode_starmap([(x,) for x in range(16)]))
+    assert (e.n, e.arg_stride, e.n_items) == (2, 64, 16)
+    e = s.from_encoded(base.encode_map(range(10, 110)))
+    assert (e.n, e.arg_stride, e.index_start, e.n_items) == (13, 0, 10, 100)
     assert s.encode_range(range(0)).n == 0 and s.encode_range(range(8)).n == 1 and s.encode_range(range(9)).n == 2
     with pytest.raises(TypeError):
         s.encode_range([1, 2, 3])
@@ -274,3 +282,47 @@ def test_bits_body_and_bit_backed_result_array():
         assert list(ra) == want.tolist() and np.array_equal(np.asarray(ra), want)
         with pytest.raises(IndexError):
             ra[n]
+
+
+def test_out_of_tree_body_registration():
+    """fbr_register_body: a body module compiled outside the library is loaded, ABI-checked and appended to
+    the body table (no device needed for that); its encoders follow the declared argument layout."""
+    from . import device_bodies as D
+    lib = _abi.load()
+    n = ctypes.c_int(0)
+    assert lib.fbr_body_count(ctypes.byref(n)) == 0 and n.value >= 15
+    s = registry.spec("collatz_steps")
+    assert s.func_id >= 13 and (s.arg_bytes, s.result_bytes, s.result_kind) == (8, 8, _abi.FBR_RES_I64)
+    assert s.flags & _abi.FBR_BODY_INDEX_ARG and registry.body_name_of(D.collatz_steps) == "collatz_steps"
+    assert s.encode_map(range(1, 10)).arg_stride == 0 and s.encode_map([3, 4]).args.tolist() == [3, 4]
+    b = registry.spec("odd_bits")
+    assert (b.arg_bytes, b.result_bytes, b.result_kind) == (8, 1, _abi.FBR_RES_BOOL)
+    fid = ctypes.c_int(-1)
+    assert lib.fbr_body_lookup(b"odd_bits", ctypes.byref(fid)) == 0 and fid.value == b.func_id
+    assert lib.fbr_register_body(b"x", b"/nonexistent.so", b"e", ctypes.byref(fid)) == _abi.FBR_ENOENT
+    # a compiled-in name cannot be taken over by a module
+    from fiber_b200 import bodies
+    so = bodies.compile_module("collatz_steps", D.COLLATZ_SRC)
+    assert lib.fbr_register_body(b"square_i64", so.encode(), b"fbr_body_entry", ctypes.byref(fid)) == _abi.FBR_EINVAL
+    with pytest.raises(RuntimeError, match="nvcc failed"):
+        bodies.compile_module("broken", "#include \"fiber_b200_body.cuh\"\nthis is not CUDA\n")
+
+
+def test_initializer_binding_and_result_layout_options():
+    with pytest.raises(NotImplementedError):
+        fiber_b200.Pool(1, initializer=print)
+    p = fiber_b200.Pool(1, initializer=W.set_parzen_samples, initargs=(np.zeros((4, 2)), np.zeros((2, 1))))
+    assert p._initializer.__fbr_init_body__ == "parzen_f64"
+    for mode in ("host", "bytes", "bits", "device"):
+        fiber_b200.Pool(1, results=mode)
+    with pytest.raises(ValueError):
+        fiber_b200.Pool(1, results="disk")
+    # parzen items may carry only h (samples from the initializer block) -- but not a mix
+    s = registry.spec("parzen_f64")
+    e = s.encode_map([0.1, 0.2])
+    assert e.shared is None and e.args.tolist() == [0.1, 0.2]
+    e = s.encode_starmap([(0.5,), (0.7,)])
+    assert e.shared is None and e.n == 2
+    xs, px = np.zeros((4, 2)), np.zeros((2, 1))
+    with pytest.raises(TypeError):
+        s.encode_starmap([(0.5,), (xs, px, 0.7)])

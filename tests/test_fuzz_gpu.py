@@ -49,6 +49,8 @@ def test_random_maps_against_oracle(ring_kib):
                 flags |= _abi.FBR_SHUFFLE
             if rng.random() < 0.3:
                 flags |= _abi.FBR_FULL_WINDOW
+            if rng.random() < 0.4:
+                flags |= _abi.FBR_VIA_RING          # task records + result ring + gather_ordered instead of direct placement
             if rng.random() < 0.2:
                 flags |= _abi.FBR_RESILIENT
                 flags &= ~_abi.FBR_SHUFFLE
@@ -110,7 +112,7 @@ def test_random_pi_ranges_bytes_and_bits(ring_kib):
     task) against the plain-C oracle: starts around 0, 2^32 and 2^40, negative and large steps, lengths that
     leave partial vectors, partial bytes and partial claim units, small rings (many waves)."""
     rng = np.random.default_rng(99 + ring_kib)
-    pools = [fiber_b200.Pool(1, ring_bytes=ring_kib << 10), fiber_b200.Pool(1, ring_bytes=ring_kib << 10, results="bits")]
+    pools = [fiber_b200.Pool(1, ring_bytes=ring_kib << 10, results="bytes"), fiber_b200.Pool(1, ring_bytes=ring_kib << 10)]
     try:
         for trial in range(30):
             n = int(rng.choice([1, 7, 8, 9, 15, 16, 17, 127, 4095, 4096, 4097, 32769, int(rng.integers(1, 200000))]))
@@ -125,6 +127,14 @@ def test_random_pi_ranges_bytes_and_bits(ring_kib):
                 assert len(res) == n and res.sum() == count, (start, n, step, cs)
                 assert np.array_equal(np.asarray(res).view(np.uint8), ref), (start, n, step, cs)
             assert np.array_equal(res.packed, np.packbits(ref, bitorder="little")), (start, n, step, cs)
+            # the same tasks as explicit argument records (a list, not a range): 8 int64 items per byte-task
+            if n <= 70000:
+                items = [start + i * step for i in range(n)]
+                for pool in pools:
+                    res = pool.map(W.is_inside, items, cs)
+                    assert len(res) == n and res.sum() == count, (start, n, step, cs)
+                    assert np.array_equal(np.asarray(res).view(np.uint8), ref), (start, n, step, cs)
+                assert np.array_equal(res.packed, np.packbits(ref, bitorder="little")), (start, n, step, cs)
     finally:
         for pool in pools:
             pool.terminate()

@@ -318,13 +318,32 @@ def test_error_callback_not_implemented(pool):              # fiber/pool.py:1162
 
 
 def test_stats_and_launch_counts():
-    pool = fiber_b200.Pool(1, timing=True)
+    """A contiguous map is placed directly by the dispatch kernel (no task records, no ring, no gather
+    launch); shuffled arrival / FBR_VIA_RING go through records + ring + gather_ordered."""
+    pool = fiber_b200.Pool(1, timing=True, results="bytes")
     pool.map(W.is_inside, range(10 ** 6))
     s = pool.stats()
     assert s["tasks_submitted"] == s["tasks_completed"] == 10 ** 6
-    assert s["dispatch_launches"] >= 1 and s["gather_launches"] >= 1
-    assert s["d2h_bytes"] >= 10 ** 6 and s["gather_bytes"] == 2 * 10 ** 6
-    assert s["dispatch_ms"] > 0 and s["gather_ms"] > 0
+    assert s["dispatch_launches"] >= 1 and s["direct_waves"] == s["dispatch_launches"] and s["gather_launches"] == 0
+    assert s["records_copied"] == 0 and s["h2d_bytes"] < 4096      # nothing but the control block goes in
+    assert s["d2h_bytes"] >= 10 ** 6 and s["dispatch_ms"] > 0
+    pool.reset_stats()
+    out, total, _ = _raw_map(pool, "pi_inside_det", 10 ** 6, _abi.FBR_WANT_SUM | _abi.FBR_VIA_RING)
+    s = pool.stats()
+    assert s["gather_launches"] >= 1 and s["direct_waves"] == 0 and s["gather_bytes"] == 2 * 10 ** 6 and s["gather_ms"] > 0
+    from oracle import cref
+    ref, count = cref.pi_inside_range(0, 10 ** 6)
+    assert np.array_equal(out, ref) and total == count
+    pool.reset_stats()
+    _raw_map(pool, "pi_inside_det", 10 ** 6, _abi.FBR_WANT_SUM | _abi.FBR_SHUFFLE)
+    s = pool.stats()
+    assert s["records_copied"] == s["units_dispatched"] > 0 and s["gather_launches"] >= 1
+    pool.terminate()
+    pool.join()
+    # default layout for bool results: one bit per task through the ordered output and PCIe
+    pool = fiber_b200.Pool(1)
+    res = pool.map(W.is_inside, range(10 ** 6))
+    assert res.packed is not None and pool.stats()["d2h_bytes"] < 10 ** 6 // 8 + 4096 and res.sum() == count
     pool.terminate()
     pool.join()
 
@@ -502,7 +521,7 @@ def test_overlapped_gather_stream_is_bit_exact():
     for k in range(3):                                  # three maps pipelined back to back
         d = _abi.MapDesc()
         d.func_id = registry.spec("pi_inside_det").func_id
-        d.flags = _abi.FBR_OUT_DEVICE | _abi.FBR_WANT_SUM
+        d.flags = _abi.FBR_OUT_DEVICE | _abi.FBR_WANT_SUM | _abi.FBR_VIA_RING    # direct placement would need no gather
         d.n_tasks, d.index_start, d.index_step, d.out = n, 0, 1, dout.value
         s = ctypes.c_uint64()
         _abi.check(lib.fbr_map_submit(h, ctypes.byref(d), ctypes.byref(s)))
@@ -608,8 +627,21 @@ def test_bit_packed_results(golden):
         assert len(r) == m and r.sum() == count, (start, m, step)
         assert np.array_equal(np.asarray(r).view(np.uint8), ref), (start, m, step)
         assert np.array_equal(r.packed, np.packbits(ref, bitorder="little")), (start, m, step)   # tail bits are zero
-    # other maps of the same pool are unaffected (non-range arguments, non-bool bodies)
-    assert pb.map(W.is_inside, list(range(100))) == arr[:100].tolist()
+    # explicit argument records (a list / an int64 array, not a range) travel one bit per result as well
+    r = pb.map(W.is_inside, list(range(100)))
+    assert r.packed is not None and r.packed.nbytes == 13 and r == arr[:100].tolist() and r.sum() == int(arr[:100].sum())
+    xs = np.arange(n, dtype=np.int64)[::-1].copy()
+    r = pb.map(W.is_inside, xs)
+    assert r.packed.nbytes == (n + 7) // 8 and r.sum() == g["count"] and np.array_equal(np.asarray(r), arr[::-1])
+    r = pb.starmap(W.is_inside, [(x,) for x in range(1003)], 5)
+    assert r.packed is not None and r == arr[:1003].tolist()
+    # results="bytes" keeps one byte per bool
+    pbytes = fiber_b200.Pool(1, results="bytes")
+    r = pbytes.map(W.is_inside, range(n))
+    assert r.packed is None and hashlib.sha256(np.asarray(r).view(np.uint8).tobytes()).hexdigest() == g["sha256_uint8"]
+    pbytes.terminate()
+    pbytes.join()
+    # non-bool bodies are unaffected
     assert pb.map(W.f, range(10)) == [i * i for i in range(10)]
     assert list(pb.imap(W.is_inside, range(1000))) == arr[:1000].tolist()
     small = fiber_b200.Pool(1, results="bits", ring_bytes=64 << 10)      # many waves: imap streams byte prefixes
@@ -625,7 +657,7 @@ def test_bit_packed_results(golden):
     assert big.packed.nbytes == 12_500_000 and big.sum() == 78540462
     ref, _ = cref.pi_inside_range(0, 10 ** 8, 1)
     assert np.array_equal(big.packed, np.packbits(ref, bitorder="little"))
-    # the raw body refuses explicit argument records
+    # explicit argument records of the raw body are 8 int64 items (64 B) per byte-task: 8 B records are refused
     lib, spec = _abi.load(), fiber_b200.registry.spec("pi_inside_bits8")
     d = _abi.MapDesc()
     d.func_id, d.n_tasks, d.arg_stride = spec.func_id, 4, 8
@@ -653,3 +685,90 @@ def test_chunk_size_blocking_tasks_run_concurrently():
     assert res == [None] * 64 and time.perf_counter() - t0 < 0.5
     pool.terminate()
     pool.join()
+
+
+# ---- out-of-tree device bodies (fbr_register_body) and the initializer block ------------------------------------
+def test_out_of_tree_bodies_bit_exact():
+    """Bodies defined in tests/device_bodies.py -- not in libfiber_b200 -- compiled to their own modules and
+    registered at run time, mapped over 1e6 ints, bit-exact against their Python definitions."""
+    from . import device_bodies as D
+    from fiber_b200 import registry
+    assert registry.spec("collatz_steps").func_id >= 13 and registry.spec("odd_bits").func_id >= 13   # past the compiled-in table
+    pool = fiber_b200.Pool(2)
+    n = 10 ** 6
+    res = pool.map(D.collatz_steps, range(1, n + 1))
+    want = D.collatz_steps_np(np.arange(1, n + 1))
+    assert np.array_equal(np.asarray(res), want) and res.sum() == int(want.sum())
+    assert res[:2000] == [D.collatz_steps(x) for x in range(1, 2001)]                # the Python definition itself
+    xs = np.random.default_rng(3).integers(1, 2 ** 40, size=100003, dtype=np.int64)
+    assert np.array_equal(np.asarray(pool.map(D.collatz_steps, xs, chunksize=7)), D.collatz_steps_np(xs))
+    assert list(pool.imap(D.collatz_steps, range(1, 500))) == [D.collatz_steps(x) for x in range(1, 500)]
+    assert pool.apply(D.collatz_steps, (27,)) == 111
+    with pytest.raises(ValueError, match="bad argument in task 3"):
+        pool.map(D.collatz_steps, [5, 6, 7, 0, 9])
+    # a registered bool body: one byte per result, placed by the same dispatch kernel template
+    ob = pool.map(D.odd_bits, range(-5000, 200000))
+    assert np.array_equal(np.asarray(ob), D.odd_bits_np(np.arange(-5000, 200000))) and ob.sum() == int(D.odd_bits_np(np.arange(-5000, 200000)).sum())
+    assert ob[:100] == [D.odd_bits(x) for x in range(-5000, -4900)]
+    # placement by index under shuffled arrival + resilient pool work for registered bodies too
+    pool.terminate()
+    pool.join()
+    rp = fiber_b200.Pool(1, error_handling=True)
+    assert np.array_equal(np.asarray(rp.map(D.collatz_steps, range(1, 50001))), want[:50000])
+    rp.terminate()
+    rp.join()
+    # registration errors
+    lib = _abi.load()
+    fid = ctypes.c_int(-1)
+    assert lib.fbr_register_body(b"nope", b"/nonexistent/libbody.so", b"fbr_body_entry", ctypes.byref(fid)) == _abi.FBR_ENOENT
+    from fiber_b200 import bodies
+    so = bodies.compile_module("collatz_steps", D.COLLATZ_SRC)
+    assert lib.fbr_register_body(b"collatz_steps", so.encode(), b"no_such_entry", ctypes.byref(fid)) == _abi.FBR_ENOENT
+    assert lib.fbr_register_body(b"other_name", so.encode(), b"fbr_body_entry", ctypes.byref(fid)) == _abi.FBR_EINVAL
+    assert lib.fbr_register_body(b"collatz_steps", so.encode(), b"fbr_body_entry", ctypes.byref(fid)) == 0   # idempotent
+    assert fid.value == registry.spec("collatz_steps").func_id
+
+
+def test_initializer_uploads_the_broadcast_block(golden):
+    """Pool(initializer=, initargs=) (fiber/pool.py:858-859): the initializer is bound to a body's broadcast
+    block, initargs are uploaded once per worker, and tasks carry only h."""
+    g = golden("parzen_102")
+    xs, px, widths = _parzen_inputs()
+    want = [(float.fromhex(h), float.fromhex(d)) for h, d in g["results_hex"]]
+    pool = fiber_b200.Pool(2, initializer=W.set_parzen_samples, initargs=(xs, px))
+    assert sorted(pool.map(W.parzen_at, widths, 1)) == want
+    assert sorted(pool.starmap(W.parzen_at, [(w,) for w in widths], 1)) == want
+    assert sorted(h.get() for h in [pool.apply_async(W.parzen_at, (w,)) for w in widths]) == want
+    assert pool.stats()["h2d_bytes"] < 2 * (xs.nbytes + 4096) + 102 * 3 * 64          # the 160 KB block went up once per device
+    pool.terminate()
+    pool.join()
+    plain = fiber_b200.Pool(1)
+    with pytest.raises(TypeError, match="no initializer block"):
+        plain.map(W.parzen_at, widths)
+    plain.terminate()
+    plain.join()
+    with pytest.raises(NotImplementedError):
+        fiber_b200.Pool(1, initializer=print)
+
+
+def test_exact_sum_and_error_caching(pool):
+    """sum() of int64 results is exact like Python's (the device folds the two 32-bit halves separately), and
+    a task error is raised again by every later get() without touching the engine."""
+    big = [3037000499, 3037000498, -3037000499, 3037000497, 5]
+    res = pool.map(W.f, big * 3)
+    assert res.sum() == sum(x * x for x in big * 3) > 2 ** 63            # each square fits int64, the total does not
+    assert sum(res.tolist()) == res.sum()
+    h = pool.map_async(W.f, [1, 2, 3037000500])
+    for _ in range(3):
+        with pytest.raises(OverflowError):
+            h.get()
+    # handles dropped without a get() release their seq (no leak of control slots / pinned segments)
+    for _ in range(300):
+        pool.map_async(W.f, range(1000))
+    import gc
+    gc.collect()
+    it = pool.imap(W.f, range(100000))
+    next(it)
+    del it
+    gc.collect()
+    assert pool.map(W.f, range(10)) == [i * i for i in range(10)]
