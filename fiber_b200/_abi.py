@@ -45,6 +45,10 @@ SYMBOLS = [
     "fbr_process_handled", "fbr_process_destroy",
     "fbr_express_last_error", "fbr_express_create", "fbr_express_submit", "fbr_express_wait", "fbr_express_discard", "fbr_express_stats",
     "fbr_express_destroy",
+    "fbr_comm_last_error", "fbr_comm_load", "fbr_comm_unique_id", "fbr_comm_create", "fbr_comm_info", "fbr_comm_sync",
+    "fbr_comm_broadcast", "fbr_comm_allgather", "fbr_comm_gather", "fbr_comm_scatter", "fbr_comm_allreduce",
+    "fbr_comm_allreduce_timed", "fbr_comm_allreduce_i64", "fbr_comm_device_alloc", "fbr_comm_device_free",
+    "fbr_comm_memcpy_h2d", "fbr_comm_memcpy_d2h", "fbr_comm_destroy",
 ]
 
 FBR_REC_NONE, FBR_REC_INT, FBR_REC_FLOAT, FBR_REC_BYTES, FBR_REC_STR = range(5)
@@ -90,7 +94,7 @@ class Stats(ctypes.Structure):
                 ("dispatch_ms", ctypes.c_double), ("gather_ms", ctypes.c_double),
                 ("gather_bytes", ctypes.c_uint64), ("dispatch_bytes", ctypes.c_uint64),
                 ("units_redispatched", ctypes.c_uint64), ("records_copied", ctypes.c_uint64),
-                ("direct_waves", ctypes.c_uint64), ("workers_respawned", ctypes.c_uint64)]
+                ("direct_waves", ctypes.c_uint64), ("workers_lost", ctypes.c_uint64)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}
@@ -179,6 +183,24 @@ def load():
         "fbr_express_discard": (i32, [vp, u64]),
         "fbr_express_stats": (i32, [vp, P(u64), P(u64), P(i32)]),
         "fbr_express_destroy": (i32, [vp]),
+        "fbr_comm_last_error": (ctypes.c_char_p, []),
+        "fbr_comm_load": (i32, [ctypes.c_char_p, P(i32)]),
+        "fbr_comm_unique_id": (i32, [vp]),
+        "fbr_comm_create": (i32, [i32, i32, i32, ctypes.c_char_p, P(vp)]),
+        "fbr_comm_info": (i32, [vp, P(i32), P(i32), P(i32)]),
+        "fbr_comm_sync": (i32, [vp]),
+        "fbr_comm_broadcast": (i32, [vp, vp, u64, i32]),
+        "fbr_comm_allgather": (i32, [vp, vp, vp, u64]),
+        "fbr_comm_gather": (i32, [vp, vp, vp, u64, i32]),
+        "fbr_comm_scatter": (i32, [vp, vp, vp, u64, i32]),
+        "fbr_comm_allreduce": (i32, [vp, vp, vp, u64, i32, i32]),
+        "fbr_comm_allreduce_timed": (i32, [vp, vp, u64, i32, i32, i32, P(ctypes.c_float)]),
+        "fbr_comm_allreduce_i64": (i32, [vp, P(ctypes.c_int64)]),
+        "fbr_comm_device_alloc": (i32, [vp, u64, P(vp)]),
+        "fbr_comm_device_free": (i32, [vp, vp]),
+        "fbr_comm_memcpy_h2d": (i32, [vp, vp, vp, u64]),
+        "fbr_comm_memcpy_d2h": (i32, [vp, vp, vp, u64]),
+        "fbr_comm_destroy": (i32, [vp]),
     }
     assert sorted(sig) == sorted(SYMBOLS)
     for name, (res, args) in sig.items():

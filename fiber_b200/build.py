@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
 SO = os.path.join(LIBDIR, "libfiber_b200.so")
-SOURCES = ["engine.cu", "queues.cu", "express.cu"]
+SOURCES = ["engine.cu", "queues.cu", "express.cu", "comm.cu"]
 HEADERS = ["kernels.cuh", "bodies.cuh", os.path.join("..", "..", "include", "fiber_b200.h")]
 
 NVCC_FLAGS = [
@@ -23,6 +23,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
     "-shared",
 ]
+LINK_FLAGS = ["-ldl"]   # body modules (fbr_register_body) and NCCL (fbr_comm_*) are bound at run time
 
 
 def nvcc():
@@ -45,7 +46,7 @@ def build(force=False, verbose=False):
         return SO
     os.makedirs(LIBDIR, exist_ok=True)
     cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        [os.path.join(CSRC, s) for s in SOURCES] + ["-o", SO]
+        [os.path.join(CSRC, s) for s in SOURCES] + ["-o", SO] + LINK_FLAGS
     subprocess.check_call(cmd)
     return SO
 

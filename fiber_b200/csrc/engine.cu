@@ -205,6 +205,8 @@ static_assert(sizeof(SeqCtrl) == 32, "");
 
 struct Worker {
     int device = -1;
+    bool dead = false;                     // the device's CUDA context took a sticky error: the worker process is gone
+    int death_error = 0;                   // cudaError_t that killed it
     int numa_node = -1;                    // host NUMA node the GPU hangs off (-1 unknown)
     int sm_count = 0;
     cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
@@ -287,6 +289,9 @@ struct SeqState {
     uint32_t redispatched_units = 0;
     fbr_map_desc_t desc;
     std::vector<SeqPart> parts;
+    std::vector<SeqPart> graveyard;        // parts that were running on a worker when it died (their blocks were re-dispatched)
+    int dead_worker = -1;                  // a worker died under this map and the map could not be re-dispatched
+    int dead_error = 0;
 };
 
 struct SharedBlock {
@@ -476,6 +481,11 @@ static int worker_init(fbr_pool* p, Worker& w, int device) {
 
 static void worker_destroy(Worker& w) {
     if (w.device < 0) return;
+    if (w.dead) {                          // a corrupted context: every call on it fails; its memory goes with the process
+        cudaGetLastError();
+        w.device = -1;
+        return;
+    }
     cudaSetDevice(w.device);
     if (w.s_in) cudaStreamSynchronize(w.s_in);
     if (w.s_comp) cudaStreamSynchronize(w.s_comp);
@@ -968,9 +978,117 @@ static int resilient_advance(fbr_pool* p, SeqState& st, SeqPart& part) {
     return rc != FBR_OK ? rc : 1;
 }
 
+// ------------------------------------------------------------------------------------------------
+// fault domain: a worker is a CUDA device; it "dies" when its context takes a sticky error (a kernel that
+// trapped, an illegal address, an ECC error, a lost device).  The reference notices dead worker processes by
+// their exit code and re-queues their pending chunks on the other workers (fiber/pool.py:1623-1656).
+// ------------------------------------------------------------------------------------------------
+// Every call on a corrupted context returns its sticky error; a healthy stream answers Success / NotReady.
+static bool worker_context_dead(Worker& w, cudaError_t* why) {
+    if (w.dead) return true;
+    cudaError_t e = cudaSetDevice(w.device);
+    if (e == cudaSuccess) e = cudaStreamQuery(w.s_comp);
+    cudaGetLastError();
+    if (e == cudaSuccess || e == cudaErrorNotReady) return false;
+    if (why) *why = e;
+    return true;
+}
+
+// contiguous, claim-unit aligned sub-blocks of tasks [first, first + count) over `workers`
+static void cut_blocks(fbr_pool* p, const BodyEntry& body, const fbr_map_desc_t& d, uint64_t first, uint64_t count,
+                       const std::vector<int>& workers, uint32_t attempt, std::vector<SeqPart>& out) {
+    const int nw = (int)workers.size();
+    if (nw == 0 || count == 0) return;
+    const uint32_t cs = d.chunksize ? d.chunksize : 32u;
+    const uint32_t unit = pick_unit(body, cs, (count + nw - 1) / nw, p->workers[workers[0]].sm_count, p->ring_bytes);
+    const uint64_t units_total = (count + unit - 1) / unit;
+    const uint64_t units_per = (units_total + nw - 1) / nw;
+    for (int i = 0; i < nw; ++i) {
+        const uint64_t b0 = std::min<uint64_t>(count, (uint64_t)i * units_per * unit);
+        const uint64_t b1 = std::min<uint64_t>(count, (uint64_t)(i + 1) * units_per * unit);
+        if (b1 <= b0) continue;
+        SeqPart part;
+        part.worker = workers[i];
+        part.first = first + b0;
+        part.count = b1 - b0;
+        part.attempt = attempt;
+        out.push_back(std::move(part));
+    }
+}
+
+static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry& body);
+
+// Worker `wi` is dead.  Maps that asked for ResilientZPool semantics get the blocks it was working on cut
+// over the surviving workers and re-dispatched with attempt + 1 (whole blocks: what a dead context had
+// finished cannot be asked any more); other maps are failed (a plain ZPool map whose worker dies never
+// returns, fiber/pool.py:801-824 -- here it raises).  The pool keeps serving on the survivors.
+static void on_worker_death(fbr_pool* p, int wi, cudaError_t err) {
+    Worker& w = p->workers[wi];
+    if (w.dead) return;
+    w.dead = true;
+    w.death_error = (int)err;
+    p->stats.workers_lost++;
+    cudaGetLastError();
+    std::vector<int> live;
+    for (size_t i = 0; i < p->workers.size(); ++i)
+        if (!p->workers[i].dead) live.push_back((int)i);
+    std::vector<uint64_t> ids;
+    for (auto& kv : p->seqs) ids.push_back(kv.first);
+    for (uint64_t id : ids) {
+        auto it = p->seqs.find(id);
+        if (it == p->seqs.end()) continue;
+        SeqState& st = *it->second;
+        if (st.finished || st.dead_worker >= 0) continue;
+        bool touched = false;
+        for (auto& part : st.parts) touched |= part.worker == wi;
+        if (!touched) continue;
+        // device-resident arguments / outputs of a map live on worker 0
+        const bool on_w0 = (st.flags & (FBR_ARGS_DEVICE | FBR_OUT_DEVICE)) != 0;
+        if (!(st.flags & FBR_RESILIENT) || live.empty() || (on_w0 && p->workers[0].dead)) {
+            st.dead_worker = wi;
+            st.dead_error = (int)err;
+            continue;
+        }
+        const BodyEntry& body = *body_of(st.func_id);
+        std::vector<SeqPart> next;
+        for (auto& part : st.parts) {
+            if (part.worker != wi) { next.push_back(std::move(part)); continue; }
+            cut_blocks(p, body, st.desc, part.first, part.count, live, part.attempt + 1, next);
+            st.redispatched_units += (uint32_t)((part.count + std::max<uint32_t>(1, part.cx.unit) - 1) / std::max<uint32_t>(1, part.cx.unit));
+            st.graveyard.push_back(std::move(part));
+        }
+        st.parts.swap(next);
+        for (size_t i = 0; i < st.parts.size(); ++i) {
+            SeqPart& part = st.parts[i];
+            if (part.ctrl_slot >= 0) continue;            // submitted before
+            const int pw = part.worker;
+            if (p->workers[pw].dead) continue;            // re-cut by a nested call below
+            if (submit_part(p, st, part, body) != FBR_OK) {
+                cudaError_t why = cudaSuccess;
+                if (worker_context_dead(p->workers[pw], &why)) {
+                    on_worker_death(p, pw, why);          // a survivor turned out dead as well: cut again (st.parts changes)
+                    i = (size_t)-1;                       // restart: submit whatever is still unsubmitted
+                    if (st.dead_worker >= 0) break;
+                } else {
+                    st.dead_worker = wi;                  // a real submission error: fail the map
+                    st.dead_error = (int)err;
+                    break;
+                }
+            }
+        }
+    }
+}
+
 static void free_seq(fbr_pool* p, SeqState& st) {
+    for (auto& part : st.graveyard)        // device-side resources died with the worker's context
+        if (part.h_lost) cudaFreeHost(part.h_lost);
+    st.graveyard.clear();
     for (auto& part : st.parts) {
         Worker& w = p->workers[part.worker];
+        if (w.dead) {                      // nothing on a dead context can be freed (or needs to be)
+            if (part.h_lost) cudaFreeHost(part.h_lost);
+            continue;
+        }
         cudaSetDevice(w.device);
         if (part.done) { cudaEventSynchronize(part.done); cudaEventDestroy(part.done); }
         for (auto e : part.wave_done) cudaEventDestroy(e);
@@ -1294,59 +1412,63 @@ int fbr_map_submit(fbr_pool_t* p, const fbr_map_desc_t* d, uint64_t* seq_out) {
     if ((d->flags & FBR_WANT_SUM) && !(body.flags & FBR_BODY_SUMMABLE))
         return fail(FBR_EINVAL, "body %s results cannot be summed", body.name.c_str());
 
-    std::unique_ptr<SeqState> st(new SeqState());
-    st->seq = ++p->next_seq;
-    st->n_tasks = d->n_tasks;
-    st->func_id = d->func_id;
-    st->flags = d->flags;
-    st->result_bytes = body.result_bytes;
-    st->result_kind = body.result_kind;
-    st->out = d->out;
-    st->desc = *d;
-    const bool need_segment = !st->out && d->n_tasks && !(d->flags & FBR_RESULTS_ON_DEVICE);
-    if (need_segment && p->workers.size() == 1) {
-        int rc = pinned_acquire(p, d->n_tasks * body.result_bytes, &st->out);
-        if (rc != FBR_OK) return rc;
-        st->own_out = true;
-    }
-
-    // contiguous task blocks per worker, cut on claim-unit boundaries (block partition ==
-    // PUSH round-robin with chunk = block)
-    const int nw = (int)p->workers.size();
-    const uint32_t cs = d->chunksize ? d->chunksize : 32u;
-    const uint32_t unit = pick_unit(body, cs, (d->n_tasks + nw - 1) / nw, p->workers[0].sm_count, p->ring_bytes);
-    const uint64_t units_total = (d->n_tasks + unit - 1) / unit;
-    const uint64_t units_per = (units_total + nw - 1) / nw;
-    for (int wi = 0; wi < nw && d->n_tasks; ++wi) {
-        const uint64_t b0 = std::min<uint64_t>(d->n_tasks, (uint64_t)wi * units_per * unit);
-        const uint64_t b1 = std::min<uint64_t>(d->n_tasks, (uint64_t)(wi + 1) * units_per * unit);
-        if (b1 <= b0) continue;
-        SeqPart part;
-        part.worker = wi;
-        part.first = b0;
-        part.count = b1 - b0;
-        st->parts.push_back(part);
-    }
-    if (need_segment && p->workers.size() > 1) {
-        // several GPUs fill one segment: bind each worker's block to its GPU's NUMA node
-        std::vector<NumaBlock> blocks;
-        for (auto& part : st->parts)
-            blocks.push_back({part.first * body.result_bytes, part.count * body.result_bytes, p->workers[part.worker].numa_node});
-        int rc = numa_pinned_acquire(p, d->n_tasks * body.result_bytes, blocks, &st->out);
-        if (rc != FBR_OK) return rc;
-        st->own_out = true;
-    }
-    for (auto& part : st->parts) {
-        int rc = submit_part(p, *st, part, body);
-        if (rc != FBR_OK) {
-            free_seq(p, *st);
-            return rc;
+    // A submission can find out that a worker has died (its context rejects every call): the worker is
+    // retired, maps in flight are re-dispatched or failed (on_worker_death) and this map is cut again over
+    // the survivors -- at most once per worker.
+    for (size_t round = 0; round <= p->workers.size(); ++round) {
+        std::vector<int> live;
+        for (size_t i = 0; i < p->workers.size(); ++i)
+            if (!p->workers[i].dead) live.push_back((int)i);
+        if (live.empty()) return fail(FBR_ECUDA, "every worker of this pool has died (last CUDA error: %s)",
+                                      cudaGetErrorString((cudaError_t)p->workers[0].death_error));
+        if (dev_mode && p->workers[0].dead)
+            return fail(FBR_ECUDA, "worker 0, which holds the device-resident arguments / output, has died");
+        std::unique_ptr<SeqState> st(new SeqState());
+        st->seq = ++p->next_seq;
+        st->n_tasks = d->n_tasks;
+        st->func_id = d->func_id;
+        st->flags = d->flags;
+        st->result_bytes = body.result_bytes;
+        st->result_kind = body.result_kind;
+        st->out = d->out;
+        st->desc = *d;
+        const bool need_segment = !st->out && d->n_tasks && !(d->flags & FBR_RESULTS_ON_DEVICE);
+        if (need_segment && live.size() == 1) {
+            int rc = pinned_acquire(p, d->n_tasks * body.result_bytes, &st->out);
+            if (rc != FBR_OK) return rc;
+            st->own_out = true;
         }
+        // contiguous task blocks per live worker, cut on claim-unit boundaries (block partition ==
+        // PUSH round-robin with chunk = block)
+        cut_blocks(p, body, *d, 0, d->n_tasks, live, 0, st->parts);
+        if (need_segment && live.size() > 1) {
+            // several GPUs fill one segment: bind each worker's block to its GPU's NUMA node
+            std::vector<NumaBlock> blocks;
+            for (auto& part : st->parts)
+                blocks.push_back({part.first * body.result_bytes, part.count * body.result_bytes, p->workers[part.worker].numa_node});
+            int rc = numa_pinned_acquire(p, d->n_tasks * body.result_bytes, blocks, &st->out);
+            if (rc != FBR_OK) return rc;
+            st->own_out = true;
+        }
+        int failed_worker = -1, rc = FBR_OK;
+        for (auto& part : st->parts) {
+            rc = submit_part(p, *st, part, body);
+            if (rc != FBR_OK) { failed_worker = part.worker; break; }
+        }
+        if (rc == FBR_OK) {
+            p->stats.tasks_submitted += d->n_tasks;
+            *seq_out = st->seq;
+            p->seqs[st->seq] = std::move(st);
+            return FBR_OK;
+        }
+        const std::string msg = g_err;
+        cudaError_t why = cudaSuccess;
+        const bool died = worker_context_dead(p->workers[failed_worker], &why);
+        if (died) on_worker_death(p, failed_worker, why);   // before free_seq: its parts on that worker are skipped
+        free_seq(p, *st);
+        if (!died) { g_err = msg; return rc; }
     }
-    p->stats.tasks_submitted += d->n_tasks;
-    *seq_out = st->seq;
-    p->seqs[st->seq] = std::move(st);
-    return FBR_OK;
+    return fail(FBR_ECUDA, "submission kept failing while workers died");
 }
 
 static void harvest(fbr_pool* p, SeqState& st) {
@@ -1384,42 +1506,78 @@ static void harvest(fbr_pool* p, SeqState& st) {
     p->stats.units_redispatched += st.redispatched_units;
 }
 
+// the map cannot complete: a worker died under it and it was not (or could not be) re-dispatched
+static int dead_map_error(fbr_pool* p, const SeqState& st) {
+    return fail(FBR_ECUDA, "worker %d (CUDA device %d) died under map %llu: %s; %s", st.dead_worker, p->workers[st.dead_worker].device,
+                (unsigned long long)st.seq, cudaGetErrorString((cudaError_t)st.dead_error),
+                (st.flags & FBR_RESILIENT) ? "no surviving worker could take its blocks over"
+                                           : "the pool was created without error_handling, so its blocks are not re-dispatched");
+}
+
 int fbr_result_wait(fbr_pool_t* p, uint64_t seq, int timeout_ms, fbr_result_t* res) {
     if (!p || !res) return fail(FBR_EINVAL, "NULL argument");
     const auto deadline = std::chrono::steady_clock::now() + std::chrono::milliseconds(timeout_ms < 0 ? 0 : timeout_ms);
     for (;;) {
-        std::vector<std::pair<int, cudaEvent_t>> evs;
+        struct Ev { int worker, device; cudaEvent_t ev; };
+        std::vector<Ev> evs;
         {
             std::lock_guard<std::mutex> g(p->mu);
             auto it = p->seqs.find(seq);
             if (it == p->seqs.end()) return fail(FBR_ENOENT, "unknown seq %llu", (unsigned long long)seq);
-            for (auto& part : it->second->parts) evs.push_back({p->workers[part.worker].device, part.done});
+            if (it->second->dead_worker >= 0) return dead_map_error(p, *it->second);
+            for (auto& part : it->second->parts) evs.push_back({part.worker, p->workers[part.worker].device, part.done});
         }
         // block outside the pool lock so other threads can keep submitting
+        bool again = false;
         for (auto& e : evs) {
-            CK(cudaSetDevice(e.first));
-            if (timeout_ms < 0) {
-                CK(cudaEventSynchronize(e.second));
-            } else {
-                for (;;) {
-                    cudaError_t q = cudaEventQuery(e.second);
-                    if (q == cudaSuccess) break;
-                    if (q != cudaErrorNotReady) return fail(FBR_ECUDA, "cudaEventQuery: %s", cudaGetErrorString(q));
-                    if (std::chrono::steady_clock::now() >= deadline) return fail(FBR_ETIMEOUT, "timeout waiting for seq %llu", (unsigned long long)seq);
-                    std::this_thread::sleep_for(std::chrono::microseconds(50));
+            cudaError_t q = cudaSetDevice(e.device);
+            if (q == cudaSuccess) {
+                if (timeout_ms < 0) {
+                    q = cudaEventSynchronize(e.ev);
+                } else {
+                    for (;;) {
+                        q = cudaEventQuery(e.ev);
+                        if (q != cudaErrorNotReady) break;
+                        if (std::chrono::steady_clock::now() >= deadline) return fail(FBR_ETIMEOUT, "timeout waiting for seq %llu", (unsigned long long)seq);
+                        std::this_thread::sleep_for(std::chrono::microseconds(50));
+                    }
                 }
             }
+            if (q != cudaSuccess) {
+                // watchdog: is it the worker (sticky context error) or just this call?
+                cudaGetLastError();
+                std::lock_guard<std::mutex> g(p->mu);
+                cudaError_t why = q;
+                if (!worker_context_dead(p->workers[e.worker], &why))
+                    return fail(FBR_ECUDA, "waiting for seq %llu on worker %d: %s", (unsigned long long)seq, e.worker, cudaGetErrorString(q));
+                on_worker_death(p, e.worker, why);
+                again = true;       // the map's parts changed (re-dispatched) or it is marked dead
+                break;
+            }
         }
+        if (again) continue;
         std::lock_guard<std::mutex> g(p->mu);
         auto it = p->seqs.find(seq);
         if (it == p->seqs.end()) return fail(FBR_ENOENT, "seq released while waiting");
         SeqState& st = *it->second;
+        if (st.dead_worker >= 0) return dead_map_error(p, st);
         // resilient maps: the round is over; re-dispatch what was lost, or copy the window back
         int more = 0;
-        for (auto& part : st.parts) {
-            if (cudaEventQuery(part.done) != cudaSuccess) { more = 1; continue; }  // replaced by another waiter
-            int rc = resilient_advance(p, st, part);
-            if (rc < 0) return rc;
+        for (size_t i = 0; i < st.parts.size(); ++i) {
+            SeqPart& part = st.parts[i];
+            Worker& w = p->workers[part.worker];
+            cudaError_t q = w.dead ? cudaErrorUnknown : cudaSetDevice(w.device);
+            if (q == cudaSuccess) q = cudaEventQuery(part.done);
+            if (q == cudaErrorNotReady) { cudaGetLastError(); more = 1; continue; }  // re-recorded by another waiter
+            int rc = q == cudaSuccess ? resilient_advance(p, st, part) : FBR_ECUDA;
+            if (rc < 0) {
+                const std::string msg = g_err;
+                cudaError_t why = q;
+                if (!worker_context_dead(w, &why)) { g_err = msg; return rc; }
+                on_worker_death(p, part.worker, why);     // st.parts is a different vector now
+                more = 1;
+                break;
+            }
             more |= rc;
         }
         if (more) continue;
@@ -1447,26 +1605,46 @@ int fbr_result_poll(fbr_pool_t* p, uint64_t seq, uint64_t* n_done) {
     std::lock_guard<std::mutex> g(p->mu);
     auto it = p->seqs.find(seq);
     if (it == p->seqs.end()) return fail(FBR_ENOENT, "unknown seq %llu", (unsigned long long)seq);
+    SeqState& st = *it->second;
+    if (st.dead_worker >= 0) return dead_map_error(p, st);
     // ordered progress: tasks [0, n_done) are final.  Blocks are contiguous per worker, so count
     // complete waves worker by worker and stop at the first incomplete one.
     uint64_t done = 0;
-    for (auto& part : it->second->parts) {
-        CK(cudaSetDevice(p->workers[part.worker].device));
+    for (size_t pi = 0; pi < st.parts.size(); ++pi) {
+        SeqPart& part = st.parts[pi];
+        Worker& w = p->workers[part.worker];
+        cudaError_t q = w.dead ? cudaErrorUnknown : cudaSetDevice(w.device);
+        if (q == cudaSuccess) q = cudaEventQuery(part.done);
+        if (q != cudaSuccess && q != cudaErrorNotReady) {
+            // watchdog (same as fbr_result_wait): a dead worker's blocks move to the survivors
+            cudaGetLastError();
+            cudaError_t why = q;
+            if (!worker_context_dead(w, &why)) return fail(FBR_ECUDA, "polling seq %llu on worker %d: %s", (unsigned long long)seq, part.worker, cudaGetErrorString(q));
+            on_worker_death(p, part.worker, why);
+            if (st.dead_worker >= 0) return dead_map_error(p, st);
+            break;                                        // progress so far stands; the next poll sees the new parts
+        }
+        cudaGetLastError();
+        const bool part_finished = q == cudaSuccess;
         if (part.cx.resilient) {
             // results become visible only once no unit is lost any more; polling drives the rounds
-            if (cudaEventQuery(part.done) == cudaSuccess) {
+            if (part_finished) {
                 if (part.finalized) { done += part.count; continue; }
-                int rc = resilient_advance(p, *it->second, part);
-                if (rc < 0) return rc;
+                int rc = resilient_advance(p, st, part);
+                if (rc < 0) {
+                    const std::string msg = g_err;
+                    cudaError_t why = cudaSuccess;
+                    if (!worker_context_dead(w, &why)) { g_err = msg; return rc; }
+                    on_worker_death(p, part.worker, why);
+                    if (st.dead_worker >= 0) return dead_map_error(p, st);
+                }
             }
-            cudaGetLastError();
             break;
         }
         uint64_t part_done = 0;
         if (part.cx.full_window && !part.cx.out_dev && !part.cx.keep_on_device) {
             // the window reaches the host in one copy at the end: nothing is final before that
-            if (cudaEventQuery(part.done) == cudaSuccess) { done += part.count; continue; }
-            cudaGetLastError();
+            if (part_finished) { done += part.count; continue; }
             break;
         }
         for (size_t i = 0; i < part.wave_done.size(); ++i) {

@@ -11,17 +11,29 @@ runs ``initializer(ring)`` and then ``func(rank, size)``.  Differences, by const
   rank in place;
 * the rendezvous a node publishes is the ``MASTER_ADDR:MASTER_PORT`` NCCL bootstraps from (the
   reference publishes ip/port for gloo, examples/ring.py:163-171);
-* ``torch_ring_init`` is the stock initializer: ``init_process_group("nccl")`` on GPUs (gloo on
-  CPU-only hosts, used by the CPU tests); the collective of the reference demo
-  (``dist.all_reduce(param.grad.data, SUM)``, examples/ring.py:81-86) then runs as
-  ``ncclAllReduce`` over NVLink/NVSwitch.
+* ``engine_ring_init`` is the B200 initializer: the member table carries the 128-byte NCCL bootstrap id
+  (``RingNode.comm_id``, made by ``Ring.run`` before the nodes start) and every node builds its communicator
+  through the C ABI (``fbr_comm_create`` = ``ncclCommInitRank``); the collective of the reference demo
+  (``dist.all_reduce(param.grad.data, SUM)``, examples/ring.py:81-86) is then ``ring_comm().allreduce`` =
+  ``ncclAllReduce`` over NVLink/NVSwitch, with no torch on the path;
+* ``torch_ring_init`` keeps the reference's own route for hosts without a GPU (gloo; the CPU tests) and for
+  code written against ``torch.distributed``: ``init_process_group("nccl")`` on GPUs.
 """
 import multiprocessing as mp
 import os
 import socket
 import time
 
-__all__ = ["Ring", "RingNode", "torch_ring_init", "allreduce_bench"]
+__all__ = ["Ring", "RingNode", "torch_ring_init", "engine_ring_init", "ring_comm", "allreduce_bench"]
+
+_comm = None          # this node's engine communicator (engine_ring_init)
+
+
+def ring_comm():
+    """The node's ``fiber_b200.comm.Comm`` once ``engine_ring_init`` has run."""
+    if _comm is None:
+        raise RuntimeError("this ring node has no engine communicator (initializer was not engine_ring_init)")
+    return _comm
 
 
 class RingNode:
@@ -32,6 +44,7 @@ class RingNode:
         self.connected = False
         self.ip = None
         self.port = None
+        self.comm_id = None       # NCCL bootstrap id (128 bytes) published by rank 0: the B200 ring's "address"
 
 
 def _free_port():
@@ -81,6 +94,9 @@ class Ring:
             self._target()
             return
         self._master = ("127.0.0.1", _free_port())
+        if self.initializer is engine_ring_init:
+            from .. import comm as _c
+            self.members[0].comm_id = _c.unique_id()      # travels to every node with the pickled member table
         ctx = mp.get_context("spawn")
         procs = [ctx.Process(target=self._child, args=(i,)) for i in range(self.size)]
         for p in procs:
@@ -113,6 +129,36 @@ def torch_ring_init(ring):
         dist.init_process_group("nccl", rank=ring.rank, world_size=ring.size, device_id=torch.device("cuda", local))
     else:
         dist.init_process_group("gloo", rank=ring.rank, world_size=ring.size)
+
+
+def engine_ring_init(ring):
+    """B200 initializer: join the NCCL communicator whose bootstrap id rank 0 published in the member table
+    (``fbr_comm_create`` -> ``ncclCommInitRank``), one node per GPU.  Under ``torchrun`` (no parent that could
+    have filled the table) the id travels through a c10d TCPStore next to the rendezvous port."""
+    global _comm
+    from .. import comm as _c
+    local = int(os.environ.get("LOCAL_RANK", ring.rank))
+    cid = ring.members[0].comm_id
+    if cid is None:
+        import datetime
+        import torch.distributed as dist
+        store = dist.TCPStore(os.environ.get("MASTER_ADDR", "127.0.0.1"), int(os.environ.get("MASTER_PORT", "29500")) + 17,
+                              ring.size, is_master=(ring.rank == 0), timeout=datetime.timedelta(seconds=120))
+        if ring.rank == 0:
+            store.set("fbr_ring_id", _c.unique_id())
+        cid = bytes(store.get("fbr_ring_id"))
+        ring.members[0].comm_id = cid
+    ndev = _device_count()
+    _comm = _c.Comm(local % max(1, ndev), ring.size, ring.rank, cid)
+    ring.members[ring.rank].connected = True
+
+
+def _device_count():
+    import ctypes
+    from .. import _abi
+    n = ctypes.c_int(0)
+    _abi.check(_abi.load().fbr_device_count(ctypes.byref(n)))
+    return n.value
 
 
 def allreduce_bench(n_elements, steps=10, warmup=3, device=None):

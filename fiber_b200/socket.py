@@ -12,16 +12,17 @@ import threading
 
 from .queues import Connection, _Queue
 
-_registry = {}                 # address token -> (_Queue forward, _Queue backward)
+_registry = {}                 # address token -> ((_Queue forward, _Queue backward), upstream): duplex sockets that connect
+                               # to an `upstream` address send forward / receive backward, the others the reverse
 _registry_lock = threading.Lock()
 _tokens = itertools.count(1)
 MODES = ("r", "w", "rw", "req", "rep")
 
 
-def _publish(pair):
+def _publish(pair, upstream=False):
     with _registry_lock:
         addr = "lane://%d" % next(_tokens)
-        _registry[addr] = pair
+        _registry[addr] = (pair, upstream)
         return addr
 
 
@@ -94,15 +95,20 @@ class LaneContext(SockContext):
     @staticmethod
     def connect(sock, addr):
         sock.addr = addr
-        sock._attach(_lookup(addr), binder=False)
+        pair, upstream = _lookup(addr)
+        # a duplex socket on the inbound side of a device talks in the same direction a binder would
+        sock._attach(pair, binder=upstream)
 
     def device(self, s1_mode, s2_mode):
         """Forwarder between an inbound and an outbound endpoint.  Returns ``(device, in_addr,
         out_addr)`` like fiber/socket.py:352-366: writers connect to ``in_addr``, readers to
         ``out_addr``; for duplex modes the second direction flows the other way."""
         q_fwd, q_back = _Queue(), _Queue()
-        in_addr = _publish((q_fwd, q_back))       # "w"/"rw" sockets connecting here send into q_fwd
-        out_addr = _publish((q_fwd, q_back))      # "r" sockets connecting here read q_fwd
+        # in_addr side: "w"/"rw" sockets send into q_fwd, "rw" sockets read q_back;
+        # out_addr side: "r"/"rw" sockets read q_fwd, "rw" sockets send into q_back (the duplex Pipe of
+        # fiber/queues.py:272 is ProcessDevice("rw", "rw") with one socket on each address)
+        in_addr = _publish((q_fwd, q_back), upstream=True)
+        out_addr = _publish((q_fwd, q_back), upstream=False)
         return _Device(), in_addr, out_addr
 
 

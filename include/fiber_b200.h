@@ -256,7 +256,8 @@ typedef struct fbr_stats {
     uint64_t units_redispatched;        /* lost units re-queued by resilient maps (pending-table resubmits) */
     uint64_t records_copied;            /* task records written to the pinned ring and copied to the device */
     uint64_t direct_waves;              /* waves whose dispatch kernel stored at the final index (no gather) */
-    uint64_t workers_respawned;         /* workers whose CUDA context died and was rebuilt (resilient pools) */
+    uint64_t workers_lost;              /* workers retired because their CUDA context died (sticky error); maps with
+                                           FBR_RESILIENT had their blocks re-dispatched to the surviving workers */
 } fbr_stats_t;
 int fbr_pool_stats(fbr_pool_t* pool, fbr_stats_t* stats);
 int fbr_pool_stats_reset(fbr_pool_t* pool);
@@ -321,6 +322,37 @@ int fbr_express_wait(fbr_express_t* x, uint64_t ticket, void* result, uint32_t* 
 int fbr_express_discard(fbr_express_t* x, uint64_t ticket);   /* handle dropped without a wait: forget the response */
 int fbr_express_stats(fbr_express_t* x, uint64_t* served, uint64_t* launches, int* resident);
 int fbr_express_destroy(fbr_express_t* x);
+
+/* ---- engine-level collectives: one process per GPU (fiber/experimental/ring.py:44-129) ---------
+ * The map shards by contiguous task block with no data-path collective; what surrounds it does exchange data:
+ * shared arguments that live on one rank (ncclBroadcast), an input array resident on one rank (scatter =
+ * grouped ncclSend/ncclRecv: the fan-out of fiber/pool.py:910-914), the ordered result blocks (ncclAllGather, or
+ * grouped send/recv to a root: the fan-in of fiber/pool.py:916-920), scalar folds (ncclAllReduce int64) and
+ * experimental.Ring's all-reduce (examples/ring.py:81-86).  A communicator is bound to one CUDA device and owns
+ * one stream; calls enqueue on it, fbr_comm_sync waits.  The 128-byte bootstrap id (ncclUniqueId) is what a ring
+ * node publishes in the member table instead of the reference's ip/port.  NCCL is dlopen()ed on first use. */
+typedef struct fbr_comm fbr_comm_t;
+#define FBR_COMM_ID_BYTES 128
+typedef enum fbr_dtype { FBR_DT_U8 = 0, FBR_DT_I32 = 1, FBR_DT_I64 = 2, FBR_DT_F32 = 3, FBR_DT_F64 = 4 } fbr_dtype;
+typedef enum fbr_redop { FBR_OP_SUM = 0, FBR_OP_PROD = 1, FBR_OP_MAX = 2, FBR_OP_MIN = 3 } fbr_redop;
+const char* fbr_comm_last_error(void);
+int fbr_comm_load(const char* libnccl_path, int* version);          /* optional: pick the NCCL build; reports its version */
+int fbr_comm_unique_id(void* id128);                                 /* rank 0: ncclGetUniqueId */
+int fbr_comm_create(int device_id, int nranks, int rank, const void* id128, fbr_comm_t** comm);   /* ncclCommInitRank */
+int fbr_comm_info(fbr_comm_t* comm, int* rank, int* nranks, int* device_id);
+int fbr_comm_sync(fbr_comm_t* comm);
+int fbr_comm_broadcast(fbr_comm_t* comm, void* dptr, uint64_t bytes, int root);
+int fbr_comm_allgather(fbr_comm_t* comm, const void* send, void* recv, uint64_t bytes_per_rank);
+int fbr_comm_gather(fbr_comm_t* comm, const void* send, void* recv_on_root, uint64_t bytes_per_rank, int root);
+int fbr_comm_scatter(fbr_comm_t* comm, const void* send_on_root, void* recv, uint64_t bytes_per_rank, int root);
+int fbr_comm_allreduce(fbr_comm_t* comm, const void* send, void* recv, uint64_t count, int dtype, int op);
+int fbr_comm_allreduce_timed(fbr_comm_t* comm, void* buf, uint64_t count, int dtype, int op, int iters, float* ms_per_call);
+int fbr_comm_allreduce_i64(fbr_comm_t* comm, int64_t* value);       /* host scalar in, global sum out (the pi count) */
+int fbr_comm_device_alloc(fbr_comm_t* comm, uint64_t bytes, void** dptr);
+int fbr_comm_device_free(fbr_comm_t* comm, void* dptr);
+int fbr_comm_memcpy_h2d(fbr_comm_t* comm, void* dptr, const void* src, uint64_t bytes);
+int fbr_comm_memcpy_d2h(fbr_comm_t* comm, void* dst, const void* dptr, uint64_t bytes);
+int fbr_comm_destroy(fbr_comm_t* comm);
 
 #ifdef __cplusplus
 }

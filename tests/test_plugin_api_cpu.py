@@ -108,6 +108,23 @@ def test_process_device_forwarder():                             # fiber/socket.
     for k in range(6):
         writers[k % 2].send(k)
     assert sorted(reader.recv(5) for _ in range(6)) == list(range(6))
+    # the duplex device the reference builds its Pipe on (fiber/queues.py:272): one "rw" socket per address,
+    # messages flow both ways
+    dd = ProcessDevice("rw", "rw", ctx=LaneContext())
+    dd.start()
+    a, b = Socket(mode="rw"), Socket(mode="rw")
+    a.connect(dd.in_addr)
+    b.connect(dd.out_addr)
+    a.send(b"hi")
+    assert b.recv(5) == b"hi"
+    b.send(b"there")
+    assert a.recv(5) == b"there"
+    for k in range(5):
+        a.send(k)
+        b.send(-k)
+    assert [b.recv(5) for _ in range(5)] == [0, 1, 2, 3, 4] and [a.recv(5) for _ in range(5)] == [0, -1, -2, -3, -4]
+    for sck in (a, b, reader, *writers):
+        sck.close()
 
 
 def test_config_precedence_and_knobs(monkeypatch):              # tests/test_config.py:18-55
