@@ -205,6 +205,13 @@ class Dist:
                 os.close(saved)
         if want_gpus != self.world and self.world > 1:
             raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (want_gpus, self.world))
+        # the engine's own communicator (fbr_comm_* = NCCL behind the C ABI) carries every exchange step that
+        # belongs to the path (count fold, scatter / gather of blocks); torch.distributed only bootstraps it
+        # (its c10d store publishes the 128-byte id) and provides the barrier of the timing bracket
+        self.comm = None
+        if self.world > 1 and backend == "nccl":
+            from fiber_b200 import comm as C
+            self.comm = C.Comm.from_store(dist.distributed_c10d._get_default_store(), self.local_rank, self.world, self.rank)
 
     def barrier(self):
         if self.world > 1:
@@ -223,6 +230,8 @@ class Dist:
     def sum_i64(self, x):
         if self.world == 1:
             return x
+        if self.comm is not None:
+            return self.comm.allreduce_i64(x)          # ncclAllReduce(sum, int64) through the C ABI
         dev = "cuda" if self.dist.get_backend() == "nccl" else "cpu"
         t = self.torch.tensor([x], dtype=self.torch.int64, device=dev)
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
@@ -233,6 +242,8 @@ class Dist:
 
     def finish(self):
         if self.world > 1:
+            if self.comm is not None:
+                self.comm.destroy()
             self.dist.destroy_process_group()
 
 
@@ -636,12 +647,17 @@ def run_multi_gpu(args, dist, dev):
         torch.cuda.synchronize()
     out.zero_()
 
+    comm = dist.comm
+    blk_bytes = width * 4096
+
     def scattered_map():
-        td.scatter(inp, list(full_in.chunk(world)) if rank == 0 else None, src=0)
-        torch.cuda.synchronize()
+        # fan-out and fan-in of the reference's master sockets (fiber/pool.py:910-920) as grouped ncclSend/ncclRecv
+        # issued by the engine's communicator; the map in between is the shard-resident one
+        comm.scatter(full_in if rank == 0 else None, inp, blk_bytes, root=0)
+        comm.sync()
         local_map()
-        td.gather(out, list(full_out.chunk(world)) if rank == 0 else None, dst=0)
-        torch.cuda.synchronize()
+        comm.gather(out, full_out if rank == 0 else None, blk_bytes, root=0)
+        comm.sync()
 
     for _ in range(2):
         scattered_map()
@@ -677,7 +693,9 @@ def run_multi_gpu(args, dist, dev):
     else:
         store.wait(["fbr_fused_done"])
     dist.barrier()
-    ar_ok, algbw, busbw, ar_ms = allreduce_bench(64 * 1024 * 1024, steps=max(5, args.steps), warmup=3, device=cuda)
+    from fiber_b200 import comm as C
+    ar_ok, algbw, busbw, ar_ms = C.allreduce_bench(comm, 64 * 1024 * 1024, steps=max(5, args.steps), warmup=3)
+    t_ok, t_algbw, t_busbw, t_ms = allreduce_bench(64 * 1024 * 1024, steps=max(5, args.steps), warmup=3, device=cuda)
     return {
         "payload4k_sharded": {
             "workload": "synthetic 4 KB-payload map, %d tasks TOTAL in contiguous blocks over %d GPUs (BASELINE.json configs[3])" % (n_total, world),
@@ -686,11 +704,14 @@ def run_multi_gpu(args, dist, dev):
                                "parity_full": ok_shard, "checked_bytes": n_total * 4096},
             "scatter_map_gather_root0": {"value": n_total * args.steps / t_sc, "unit": "tasks/s", "ms_per_step": 1e3 * t_sc / args.steps,
                                          "parity_full": ok_gathered, "checked_bytes": n_total * 4096,
-                                         "note": "NCCL scatter from rank 0 + map + NCCL gather to rank 0; root link-bound"},
+                                         "note": "fbr_comm_scatter (grouped ncclSend/ncclRecv) from rank 0 + map + fbr_comm_gather to rank 0, "
+                                                 "all through the C ABI; root link-bound"},
             "fused_peer_memory_root0": fused},
         "inprocess_pool_e2e": inproc,
         "ring_allreduce": {"workload": "all-reduce SUM of 64 Mi fp32 (256 MiB) per rank, %d ranks (BASELINE.json configs[4])" % world,
                            "bit_exact": ar_ok, "algbw_GBps": algbw, "busbw_GBps": busbw, "ms": ar_ms,
+                           "api": "fbr_comm_allreduce (ncclAllReduce behind the C ABI, bootstrap id from the ring member table)",
+                           "torch_distributed_same_buffer": {"bit_exact": t_ok, "busbw_GBps": t_busbw, "ms": t_ms},
                            "nvlink_ref": "measured refs: 725 GB/s all-reduce busbw @1 GiB, 770 GB/s peer copy (B200_PROFILING.md)"},
     }
 

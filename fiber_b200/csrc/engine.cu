@@ -860,11 +860,13 @@ static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry
         const uint64_t bytes_per_task = std::max<uint64_t>(R, cx.host_args ? d.arg_stride : 0);
         // a wave must carry enough kernel time to hide its launches: 8 MiB of byte results is ~22 us of
         // pi dispatch; a byte of bit-packed results stands for 8 tasks, so 1 MiB is the same work
-        const uint64_t min_wave_bytes = body.result_kind == FBR_RES_BITS8 ? (1ull << 20) : (8ull << 20);
+        uint64_t min_wave_bytes = body.result_kind == FBR_RES_BITS8 ? (1ull << 20) : (8ull << 20);
+        if (const char* e = getenv("FBR_MIN_WAVE_KB")) min_wave_bytes = std::max<uint64_t>(4096, (uint64_t)atoll(e) << 10);   // tuning knob
         const uint64_t min_wave_tasks = round_up(std::max<uint64_t>(1, min_wave_bytes / bytes_per_task), unit);
         // 8 waves for ~100 MB maps, up to 64 for multi-GB ones (~64 MiB per wave): the first wave's
         // H2D and the last wave's D2H are the only copies nothing overlaps with
-        const uint64_t n_waves = std::min<uint64_t>(64, std::max<uint64_t>(8, part.count * bytes_per_task / (64ull << 20)));
+        uint64_t n_waves = std::min<uint64_t>(64, std::max<uint64_t>(8, part.count * bytes_per_task / (64ull << 20)));
+        if (const char* e = getenv("FBR_WAVES")) n_waves = std::max<uint64_t>(1, (uint64_t)atoll(e));                          // tuning knob
         const uint64_t share = round_up((part.count + n_waves - 1) / n_waves, unit);
         cx.wave_tasks_cap = std::min(cx.wave_tasks_cap, std::max(min_wave_tasks, share));
     }

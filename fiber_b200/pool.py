@@ -525,7 +525,12 @@ class Pool:
             raise ValueError("Pool is not running")
 
     def _shared_handle(self, blob):
+        # the very same bytes object as last time (the encoder's block cache): no need to fingerprint 80-160 KB again
+        last = getattr(self, "_last_shared", None)
+        if last is not None and last[0] is blob and last[1] in self._shared_cache:
+            return self._shared_cache[last[1]]
         key = registry.fingerprint(blob)
+        self._last_shared = (blob, key)
         hit = self._shared_cache.get(key)
         if hit is not None:
             self._shared_cache.move_to_end(key)

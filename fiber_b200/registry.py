@@ -367,8 +367,21 @@ class _Parzen(BodySpec):
         self.elem = np.dtype(elem)
 
     def shared_block(self, x_samples, point_x):
+        """The broadcast block for (x_samples, point_x).  The reference pickles both into every one of its task
+        messages; the example submits 102 ``apply_async`` calls with the same arrays, so the last block is kept
+        and reused when the arguments compare equal (an exact memcmp of 160 KB, ~10 us, instead of casting and
+        serialising them again)."""
         xs = np.asarray(x_samples)
         px = np.asarray(point_x)
+        last = getattr(self, "_last_block", None)
+        if last is not None and last[0].shape == xs.shape and last[1].shape == px.shape and last[0].dtype == xs.dtype \
+                and np.array_equal(last[0], xs) and np.array_equal(last[1], px):
+            return last[2]
+        blob = self._build_block(xs, px)
+        self._last_block = (xs.copy(), px.copy(), blob)
+        return blob
+
+    def _build_block(self, xs, px):
         if xs.ndim != 2 or px.ndim != 2 or px.shape[0] != xs.shape[1]:
             raise TypeError("parzen_estimation: x_samples must be (n, d) and point_x (d, p)")
         if px.shape[0] > 8:

@@ -146,3 +146,23 @@ def test_config_precedence_and_knobs(monkeypatch):              # tests/test_con
         monkeypatch.delenv("FIBER_CPU_PER_JOB", raising=False)
         fiber_b200.reset()
     assert config.cpu_per_job == 1 and isinstance(fiber_b200.SimpleQueue(), fiber_b200.queues.SimpleQueuePush)
+
+
+def test_pool_multiple_workers_inside_one_job():
+    """tests/test_pool.py:160-177 of the reference sets ``cpu_per_job = 2``, starts ``Pool(4)`` and checks the
+    *process names* its tasks see: two jobs, each forking two workers (``ForkProcess-1/-2`` twice).  That pins
+    an internal of the process backend -- how ``ceil(processes / cpu_per_job)`` jobs fan out into forked worker
+    processes (fiber/pool.py:1009-1057, 1405-1408) -- which has no counterpart here: a worker is a CUDA device,
+    not a forked process inside a job, and tasks have no process name.  What survives of the contract is the job
+    arithmetic, restated here; the rest of that test is deliberately NOT restated."""
+    from fiber_b200 import config
+    old = config.cpu_per_job
+    try:
+        config.cpu_per_job = 2
+        pool = fiber_b200.Pool(4)
+        assert pool.n_jobs == 2                                   # two jobs of two workers each
+        assert [fiber_b200.pool.n_jobs(p, 2) for p in (1, 2, 3, 4, 5)] == [1, 1, 2, 2, 3]
+        config.cpu_per_job = 1
+        assert fiber_b200.Pool(4).n_jobs == 4
+    finally:
+        config.cpu_per_job = old

@@ -178,7 +178,7 @@ def test_parzen_f64_bit_exact(pool, golden):
     assert sorted(star) == want
 
 
-def test_parzen_f32_tolerance(pool, golden):
+def test_parzen_f32_tolerance(pool, golden, record_property):
     """fp32 window test (north-star): k_n may differ from fp64 only on boundary samples, i.e. those
     with | |x_d|/h - 0.5 | <= 2^-22 * max(1, |x_d|/h); density rtol 1e-6 once k_n matches."""
     from oracle import bodies as B, cref
@@ -186,7 +186,7 @@ def test_parzen_f32_tolerance(pool, golden):
     xs, px, widths = _parzen_inputs()
     star = pool.starmap(W.parzen_estimation_f32, [(xs, px, w) for w in widths], 1)
     n = len(xs)
-    mismatches = 0
+    mismatches = cpu_mismatches = 0
     for (h, dens), w, k64 in zip(star, widths, g["k_n"]):
         assert h == w
         k_gpu = int(round(dens * h * n))
@@ -194,10 +194,15 @@ def test_parzen_f32_tolerance(pool, golden):
         assert k_gpu == k32                                       # bit-exact vs same-precision oracle
         assert abs(k_gpu - k64) <= B.parzen_boundary_count(xs, px, w)
         mismatches += k_gpu != k64
+        cpu_mismatches += k32 != k64
         if k_gpu == k64:
             want = (k64 / n) / h
             assert abs(dens - want) <= 1e-6 * abs(want)
-    assert mismatches <= 2
+    # report the observed count of widths whose fp32 k_n differs from the fp64 golden value
+    record_property("parzen_f32_vs_f64_kn_mismatches", mismatches)
+    print("parzen fp32 vs fp64: %d of %d widths differ in k_n (boundary samples only; CPU fp32 restatement: %d)"
+          % (mismatches, len(widths), cpu_mismatches))
+    assert mismatches == cpu_mismatches <= 2
 
 
 # ---- synthetic 4 KB payload map ---------------------------------------------------------------------
