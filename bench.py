@@ -237,6 +237,18 @@ class Dist:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
         return int(t.item())
 
+    def sum_i64_begin(self, x):
+        """Start the global fold of one int64 per rank; `sum_i64_end` collects it.  On the engine communicator the
+        fold runs on its own stream and overlaps the next map (one fold in flight)."""
+        if self.comm is not None:
+            self.comm.allreduce_i64_begin(x)
+            self._fold = None
+        else:
+            self._fold = self.sum_i64(x)
+
+    def sum_i64_end(self):
+        return self.comm.allreduce_i64_end() if (self.comm is not None and self._fold is None) else self._fold
+
     def all_true(self, flag):
         return self.sum_i64(0 if flag else 1) == 0
 
@@ -988,16 +1000,34 @@ def run_ours(args, dist):
     my_range = range(my_first, my_first + PI_TASKS)
     e2e_counts = []
 
+    fold = {"pending": False}
+
+    def fold_count(c, sink):
+        """The job-wide count of a step: one ncclAllReduce(sum, int64) per step, started when the step's own count
+        is in hand and collected one step later, so it overlaps the next map (drained inside the timed region)."""
+        if world == 1:
+            sink.append(c)
+            return
+        if fold["pending"]:
+            sink.append(dist.sum_i64_end())
+        dist.sum_i64_begin(c)
+        fold["pending"] = True
+
+    def fold_drain(sink):
+        if fold["pending"]:
+            sink.append(dist.sum_i64_end())
+            fold["pending"] = False
+
     def e2e_step():
         res = pool.map(W.is_inside, my_range)             # blocks until the pinned result segment is final
-        c = res.sum()                                     # count folded on the device, read on the host
-        e2e_counts.append(dist.sum_i64(c) if world > 1 else c)
+        fold_count(res.sum(), e2e_counts)                 # count folded on the device, read on the host
         e2e_step.last = res
 
     for _ in range(max(args.warmup, 3)):
         e2e_step()
+    fold_drain(e2e_counts)
     pool.reset_stats()
-    t_e2e = timed_steps(dist, args.steps, 0, e2e_step, None, clocks.windows)
+    t_e2e = timed_steps(dist, args.steps, 0, e2e_step, lambda: fold_drain(e2e_counts), clocks.windows)
     se = pool.stats()
     e2e_value = world * PI_TASKS * args.steps / t_e2e
     packed = e2e_step.last.packed
@@ -1051,14 +1081,14 @@ def run_ours(args, dist):
 
     def e2e_dev_step():
         res = dpool.map(W.is_inside, my_range)
-        c = res.sum()
-        dev_counts.append(dist.sum_i64(c) if world > 1 else c)
+        fold_count(res.sum(), dev_counts)
         del res
 
     for _ in range(3):
         e2e_dev_step()
+    fold_drain(dev_counts)
     dpool.reset_stats()
-    t_e2e_dev = timed_steps(dist, args.steps, 0, e2e_dev_step, None, clocks.windows)
+    t_e2e_dev = timed_steps(dist, args.steps, 0, e2e_dev_step, lambda: fold_drain(dev_counts), clocks.windows)
     sd = dpool.stats()
     e2e["results_on_device"] = {"value": world * PI_TASKS * args.steps / t_e2e_dev, "unit": "tasks/s",
                                 "ms_per_step": 1e3 * t_e2e_dev / args.steps,
@@ -1076,14 +1106,14 @@ def run_ours(args, dist):
 
     def e2e_bytes_step():
         res = bpool.map(W.is_inside, my_range)
-        c = res.sum()
-        byte_counts.append(dist.sum_i64(c) if world > 1 else c)
+        fold_count(res.sum(), byte_counts)
         e2e_bytes_step.last = res
 
     for _ in range(3):
         e2e_bytes_step()
+    fold_drain(byte_counts)
     bpool.reset_stats()
-    t_e2e_bytes = timed_steps(dist, args.steps, 0, e2e_bytes_step, None, clocks.windows)
+    t_e2e_bytes = timed_steps(dist, args.steps, 0, e2e_bytes_step, lambda: fold_drain(byte_counts), clocks.windows)
     sb = bpool.stats()
     arr = np.asarray(e2e_bytes_step.last).view(np.uint8)
     e2e["results_byte_per_bool"] = {"value": world * PI_TASKS * args.steps / t_e2e_bytes, "unit": "tasks/s",

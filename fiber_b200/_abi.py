@@ -47,7 +47,8 @@ SYMBOLS = [
     "fbr_express_destroy",
     "fbr_comm_last_error", "fbr_comm_load", "fbr_comm_unique_id", "fbr_comm_create", "fbr_comm_info", "fbr_comm_sync",
     "fbr_comm_broadcast", "fbr_comm_allgather", "fbr_comm_gather", "fbr_comm_scatter", "fbr_comm_allreduce",
-    "fbr_comm_allreduce_timed", "fbr_comm_allreduce_i64", "fbr_comm_device_alloc", "fbr_comm_device_free",
+    "fbr_comm_allreduce_timed", "fbr_comm_allreduce_i64", "fbr_comm_allreduce_i64_begin", "fbr_comm_allreduce_i64_end",
+    "fbr_comm_device_alloc", "fbr_comm_device_free",
     "fbr_comm_memcpy_h2d", "fbr_comm_memcpy_d2h", "fbr_comm_destroy",
 ]
 
@@ -196,6 +197,8 @@ def load():
         "fbr_comm_allreduce": (i32, [vp, vp, vp, u64, i32, i32]),
         "fbr_comm_allreduce_timed": (i32, [vp, vp, u64, i32, i32, i32, P(ctypes.c_float)]),
         "fbr_comm_allreduce_i64": (i32, [vp, P(ctypes.c_int64)]),
+        "fbr_comm_allreduce_i64_begin": (i32, [vp, ctypes.c_int64]),
+        "fbr_comm_allreduce_i64_end": (i32, [vp, P(ctypes.c_int64)]),
         "fbr_comm_device_alloc": (i32, [vp, u64, P(vp)]),
         "fbr_comm_device_free": (i32, [vp, vp]),
         "fbr_comm_memcpy_h2d": (i32, [vp, vp, vp, u64]),

@@ -168,6 +168,15 @@ class Comm:
         _check(self.lib.fbr_comm_allreduce_i64(self.handle, ctypes.byref(v)))
         return int(v.value)
 
+    def allreduce_i64_begin(self, value):
+        """Enqueue the scalar fold and return: it overlaps whatever the caller does next (the next map)."""
+        _check(self.lib.fbr_comm_allreduce_i64_begin(self.handle, int(value)))
+
+    def allreduce_i64_end(self):
+        v = ctypes.c_int64(0)
+        _check(self.lib.fbr_comm_allreduce_i64_end(self.handle, ctypes.byref(v)))
+        return int(v.value)
+
     def destroy(self):
         h, self.handle = self.handle, None
         if h:

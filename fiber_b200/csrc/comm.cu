@@ -129,6 +129,9 @@ struct fbr_comm {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     long long* d_scalar = nullptr;      // device scratch for scalar folds
+    long long* h_scalar = nullptr;      // pinned: [0] value in, [1] global sum out (truly asynchronous copies)
+    cudaEvent_t ev_scalar = nullptr;
+    bool scalar_pending = false;
 };
 
 extern "C" {
@@ -171,6 +174,8 @@ int fbr_comm_create(int device_id, int nranks, int rank, const void* id128, fbr_
     CCK(cudaEventCreate(&c->ev0));
     CCK(cudaEventCreate(&c->ev1));
     CCK(cudaMalloc((void**)&c->d_scalar, 64));
+    CCK(cudaHostAlloc((void**)&c->h_scalar, 64, cudaHostAllocPortable));
+    CCK(cudaEventCreateWithFlags(&c->ev_scalar, cudaEventDisableTiming));
     ncclUniqueId id;
     memcpy(&id, id128, sizeof id);
     NCK(g_nccl.CommInitRank(&c->comm, nranks, id, rank));
@@ -262,15 +267,36 @@ int fbr_comm_allreduce_timed(fbr_comm_t* c, void* buf, uint64_t count, int dtype
     return FBR_OK;
 }
 
-/* scalar fold of one int64 per rank (the pi count): host value in, global sum out */
+/* Scalar fold of one int64 per rank (the pi count), split in two so that it overlaps the next map:
+ * _begin enqueues H2D (pinned) + ncclAllReduce(sum, int64) + D2H (pinned) on the communicator's stream and returns;
+ * _end waits for it and hands out the global sum.  One fold may be pending per communicator. */
+int fbr_comm_allreduce_i64_begin(fbr_comm_t* c, int64_t value) {
+    if (!c) return cfail(FBR_EINVAL, "NULL comm");
+    if (c->scalar_pending) return cfail(FBR_ESTATE, "a scalar fold is already pending on this communicator");
+    CCK(cudaSetDevice(c->device));
+    c->h_scalar[0] = value;
+    CCK(cudaMemcpyAsync(c->d_scalar, &c->h_scalar[0], sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    NCK(g_nccl.AllReduce(c->d_scalar, c->d_scalar, 1, ncclInt64, ncclSum, c->comm, c->stream));
+    CCK(cudaMemcpyAsync(&c->h_scalar[1], c->d_scalar, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    CCK(cudaEventRecord(c->ev_scalar, c->stream));
+    c->scalar_pending = true;
+    return FBR_OK;
+}
+int fbr_comm_allreduce_i64_end(fbr_comm_t* c, int64_t* sum) {
+    if (!c || !sum) return cfail(FBR_EINVAL, "bad arguments");
+    if (!c->scalar_pending) return cfail(FBR_ESTATE, "no scalar fold pending");
+    CCK(cudaSetDevice(c->device));
+    CCK(cudaEventSynchronize(c->ev_scalar));
+    c->scalar_pending = false;
+    *sum = c->h_scalar[1];
+    return FBR_OK;
+}
+/* host value in, global sum out */
 int fbr_comm_allreduce_i64(fbr_comm_t* c, int64_t* value) {
     if (!c || !value) return cfail(FBR_EINVAL, "bad arguments");
-    CCK(cudaSetDevice(c->device));
-    CCK(cudaMemcpyAsync(c->d_scalar, value, sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
-    NCK(g_nccl.AllReduce(c->d_scalar, c->d_scalar, 1, ncclInt64, ncclSum, c->comm, c->stream));
-    CCK(cudaMemcpyAsync(value, c->d_scalar, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
-    CCK(cudaStreamSynchronize(c->stream));
-    return FBR_OK;
+    int rc = fbr_comm_allreduce_i64_begin(c, *value);
+    if (rc != FBR_OK) return rc;
+    return fbr_comm_allreduce_i64_end(c, value);
 }
 
 /* device buffers for callers that have no pool (ring nodes): plain cudaMalloc on the communicator's device */
@@ -307,6 +333,8 @@ int fbr_comm_destroy(fbr_comm_t* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm) g_nccl.CommDestroy(c->comm);
     cudaFree(c->d_scalar);
+    cudaFreeHost(c->h_scalar);
+    if (c->ev_scalar) cudaEventDestroy(c->ev_scalar);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);

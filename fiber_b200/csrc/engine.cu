@@ -22,6 +22,8 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
 #include <deque>
 #include <memory>
 #include <mutex>
@@ -40,6 +42,8 @@ using namespace fbr;
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
 
+static int fail(int code, const char* fmt, ...);
+const std::string& last_error_of_this_thread();
 static int fail(int code, const char* fmt, ...) {
     char buf[512];
     va_list ap;
@@ -49,12 +53,45 @@ static int fail(int code, const char* fmt, ...) {
     g_err = buf;
     return code;
 }
+const std::string& last_error_of_this_thread() { return g_err; }
 #define CK(call)                                                                                  \
     do {                                                                                          \
         cudaError_t e_ = (call);                                                                  \
         if (e_ != cudaSuccess)                                                                    \
             return fail(FBR_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
+
+struct SubmitThread;
+void SubmitThread_loop_impl(SubmitThread* t);
+// One host thread per worker for submissions: the CUDA calls of different devices (stream waits, launches,
+// async copies, event records: ~50 us per part of 8 waves) run side by side instead of one after the other,
+// which is what an 8-GPU in-process pool needs to keep up with 0.25 ms kernels.
+struct SubmitThread {
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::function<int()> job;
+    bool pending = false, finished = false, quit = false;
+    int rc = 0;
+    std::string err;
+    SubmitThread() : th([this] { loop(); }) {}
+    ~SubmitThread() {
+        { std::lock_guard<std::mutex> g(mu); quit = true; }
+        cv.notify_all();
+        if (th.joinable()) th.join();
+    }
+    void loop() { SubmitThread_loop_impl(this); }
+    void post(std::function<int()> f) {
+        { std::lock_guard<std::mutex> g(mu); job = std::move(f); pending = true; finished = false; }
+        cv.notify_all();
+    }
+    int wait(std::string* msg) {
+        std::unique_lock<std::mutex> g(mu);
+        cv.wait(g, [this] { return finished; });
+        if (msg) *msg = err;
+        return rc;
+    }
+};
 
 // ------------------------------------------------------------------------------------------------
 // body table: the compiled-in bodies plus bodies registered at run time from separately compiled
@@ -98,18 +135,22 @@ static void launch_payload_map(const void* wpv, int grid, void* sv) {
         int sm = 148, dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
-        int per_sm = 2;
-        if (const char* e = getenv("FBR_DISPATCH_OCC")) per_sm = std::max(1, std::min(2, atoi(e)));
+        static const bool deep = getenv("FBR_TMA_DEEP") && atoi(getenv("FBR_TMA_DEEP")) != 0;
+        int per_sm = deep ? 1 : 2;
+        if (const char* e = getenv("FBR_DISPATCH_OCC")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
         const int g = (int)std::min<uint32_t>(wp.n_units, (uint32_t)(sm * per_sm));
-        dispatch_payload_map_tma_kernel<<<g, 160, tma_map::kSmemBytes, s>>>(wp);
+        if (deep) dispatch_payload_map_tma_kernel<6, 3><<<g, 160, tma_map::smem_bytes(6, 3), s>>>(wp);
+        else dispatch_payload_map_tma_kernel<3, 2><<<g, 160, tma_map::kSmemBytes, s>>>(wp);
         return;
     }
     dispatch_payload_map_kernel<<<grid, kThreads, 0, s>>>(wp);
 }
 static int occ_payload_map(int) {
-    cudaFuncSetAttribute(dispatch_payload_map_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_map::kSmemBytes);
+    cudaFuncSetAttribute(dispatch_payload_map_tma_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_map::kSmemBytes);
+    cudaFuncSetAttribute(dispatch_payload_map_tma_kernel<6, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_map::smem_bytes(6, 3));
     cudaFuncAttributes at;
-    cudaFuncGetAttributes(&at, (const void*)dispatch_payload_map_tma_kernel);   // force-load
+    cudaFuncGetAttributes(&at, (const void*)dispatch_payload_map_tma_kernel<3, 2>);   // force-load
+    cudaFuncGetAttributes(&at, (const void*)dispatch_payload_map_tma_kernel<6, 3>);
     return occ_of((const void*)dispatch_payload_map_kernel);
 }
 static void launch_payload_checksum(const void* wpv, int grid, void* sv) {
@@ -212,6 +253,7 @@ struct Worker {
     cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
     cudaStream_t s_gath = nullptr;         // higher-priority stream for gathers that overlap the next dispatch
     bool prev_wave_overlap = false;        // the previous wave used only its half of the ring
+    uint32_t gath_hist = 0;                // bit k: wave wno-1-k ran its gather on s_gath (its ev_comp is not ordered by s_comp)
     TaskRecord* h_records = nullptr;   // pinned task ring: kRecWindows x kRecCapacity
     TaskRecord* d_records = nullptr;   // device mirror
     SlotHeader* d_headers = nullptr;   // kRecCapacity
@@ -269,6 +311,7 @@ struct SeqPart {
     LostUnit* h_lost = nullptr;           // pinned mirror
     uint32_t lost_cap = 0, attempt = 0;
     bool finalized = false;               // resilient: window copied back to the host
+    bool first_wave_pending = true;       // the block's first wave must wait for what submit_part put on s_in
     PartCtx cx;
 };
 
@@ -305,11 +348,13 @@ struct fbr_pool {
     uint32_t flags = 0;
     uint64_t ring_bytes = 0;
     bool peer_ok = false;             // every worker can load/store every other worker's memory (NVLink P2P)
+    bool peer_checked = false;        // ... decided (and enabled) by the first map with device-resident args / output
     std::vector<Worker> workers;
     uint64_t next_seq = 0;
     std::unordered_map<uint64_t, std::unique_ptr<SeqState>> seqs;
     std::unordered_map<uint64_t, SharedBlock> shared;
     uint64_t next_shared = 1;
+    std::vector<std::unique_ptr<SubmitThread>> submitters;   // per worker, started with the first multi-worker map
     // pinned host segment cache (size class -> free blocks), and live blocks -> class
     std::unordered_map<uint64_t, std::vector<void*>> pin_free;
     std::unordered_map<void*, uint64_t> pin_live;
@@ -323,6 +368,27 @@ struct fbr_pool {
 // ------------------------------------------------------------------------------------------------
 // helpers
 // ------------------------------------------------------------------------------------------------
+// the parts of a multi-worker map are submitted from one host thread per worker: counters are added atomically
+#define STAT_ADD(p, field, v) __atomic_fetch_add(&(p)->stats.field, (uint64_t)(v), __ATOMIC_RELAXED)
+
+void SubmitThread_loop_impl(SubmitThread* t) {
+    std::unique_lock<std::mutex> g(t->mu);
+    for (;;) {
+        t->cv.wait(g, [t] { return t->pending || t->quit; });
+        if (t->quit) return;
+        std::function<int()> f = std::move(t->job);
+        t->pending = false;
+        g.unlock();
+        const int rc = f();
+        const std::string msg = rc != FBR_OK ? last_error_of_this_thread() : std::string();
+        g.lock();
+        t->rc = rc;
+        t->err = msg;
+        t->finished = true;
+        t->cv.notify_all();
+    }
+}
+
 static uint64_t round_up(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
 
 static uint64_t pin_class(uint64_t bytes) {
@@ -567,13 +633,20 @@ static int run_wave(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry& b
     TaskRecord* hrec = w.h_records + (size_t)rw * kRecCapacity;
     TaskRecord* drec = w.d_records + (size_t)rw * kRecCapacity;
 
-    // copy-in stream: wait until the device window / arg half were consumed, then H2D
-    CK(cudaStreamWaitEvent(w.s_in, w.ev_comp[rw], 0));  // wave wno-4 kernels done (device window free)
-    if (wno >= 2) CK(cudaStreamWaitEvent(w.s_in, w.ev_comp[(wno - 2) % kRecWindows], 0));  // arg half free
+    // copy-in stream: wait until the device window / arg half were consumed, then H2D.  A wave that copies
+    // nothing in (computed records, range() or device-resident arguments) skips the hop through s_in -- every
+    // cross-stream event costs the GPU a few microseconds per wave -- except the first wave of a block, which
+    // has to see the control block (and shared block) its submit_part put on s_in.
+    const bool in_copies = have_records || cx.host_args || part.first_wave_pending;
+    part.first_wave_pending = false;
+    if (in_copies) {
+        CK(cudaStreamWaitEvent(w.s_in, w.ev_comp[rw], 0));  // wave wno-4 kernels done (device window free)
+        if (wno >= 2) CK(cudaStreamWaitEvent(w.s_in, w.ev_comp[(wno - 2) % kRecWindows], 0));  // arg half free
+    }
     if (have_records) {
         CK(cudaMemcpyAsync(drec, hrec, sizeof(TaskRecord) * n_units, cudaMemcpyHostToDevice, w.s_in));
-        p->stats.h2d_bytes += sizeof(TaskRecord) * n_units;
-        p->stats.records_copied += n_units;
+        STAT_ADD(p, h2d_bytes, sizeof(TaskRecord) * n_units);
+        STAT_ADD(p, records_copied, n_units);
     }
     const uint8_t* wave_args = cx.args_full;
     if (cx.host_args) {   // streaming host arguments (contiguous waves only)
@@ -585,10 +658,10 @@ static int run_wave(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry& b
         if (bytes)
             CK(cudaMemcpyAsync(w.d_args[half], (const uint8_t*)d.args + wave_first * (uint64_t)d.arg_stride, bytes,
                                cudaMemcpyHostToDevice, w.s_in));
-        p->stats.h2d_bytes += bytes;
+        STAT_ADD(p, h2d_bytes, bytes);
         wave_args = w.d_args[half];
     }
-    CK(cudaEventRecord(w.ev_rec_h2d[rw], w.s_in));
+    if (in_copies) CK(cudaEventRecord(w.ev_rec_h2d[rw], w.s_in));
 
     // compute streams: dispatch on s_comp; gather on s_comp too, or -- overlapped waves -- on the
     // higher-priority s_gath so that it runs while the next wave's dispatch kernel computes.
@@ -597,11 +670,15 @@ static int run_wave(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry& b
     cudaStream_t s_g = ov ? w.s_gath : w.s_comp;
     uint8_t* ring_base = ov ? w.d_ring + (size_t)half * (p->ring_bytes / 2) : w.d_ring;
     SlotHeader* hdr_base = ov ? w.d_headers + (size_t)half * kRecCapacity : w.d_headers;
-    CK(cudaStreamWaitEvent(w.s_comp, w.ev_rec_h2d[rw], 0));
-    // the ring region this dispatch writes must have been drained by the gather that last read it
-    if (wno >= 1 && !(ov && w.prev_wave_overlap)) CK(cudaStreamWaitEvent(w.s_comp, w.ev_comp[(wno - 1) % kRecWindows], 0));
-    if (wno >= 2) CK(cudaStreamWaitEvent(w.s_comp, w.ev_comp[(wno - 2) % kRecWindows], 0));
+    if (in_copies) CK(cudaStreamWaitEvent(w.s_comp, w.ev_rec_h2d[rw], 0));
+    // the ring region this dispatch writes must have been drained by the gather that last read it (gathers on
+    // s_comp itself are ordered by the stream: only a gather that ran on s_gath needs the event)
+    if ((w.gath_hist & 3u) || ov) {
+        if (wno >= 1 && !(ov && w.prev_wave_overlap)) CK(cudaStreamWaitEvent(w.s_comp, w.ev_comp[(wno - 1) % kRecWindows], 0));
+        if (wno >= 2) CK(cudaStreamWaitEvent(w.s_comp, w.ev_comp[(wno - 2) % kRecWindows], 0));
+    }
     w.prev_wave_overlap = ov;
+    w.gath_hist = ((w.gath_hist << 1) | (ov ? 1u : 0u)) & 3u;
     if (!cx.full_window) CK(cudaStreamWaitEvent(w.s_comp, w.ev_out[half], 0));  // out half drained
     uint8_t* const out_window = cx.full_window ? cx.window_base : w.d_out[half];      // ordered output of this wave's window
     const uint64_t out_first = cx.full_window ? part.first : wave_first;               // map index of out_window[0]
@@ -648,12 +725,12 @@ static int run_wave(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry& b
         CK(cudaEventRecord(td.b, w.s_comp));
         part.t_dispatch.push_back(td);
     }
-    p->stats.dispatch_launches++;
-    p->stats.units_dispatched += n_units;
-    p->stats.dispatch_bytes += wt * ((uint64_t)(d.arg_stride ? body.arg_bytes : 0) + cx.R);
+    STAT_ADD(p, dispatch_launches, 1);
+    STAT_ADD(p, units_dispatched, n_units);
+    STAT_ADD(p, dispatch_bytes, wt * ((uint64_t)(d.arg_stride ? body.arg_bytes : 0) + cx.R));
 
     if (direct) {
-        p->stats.direct_waves++;
+        STAT_ADD(p, direct_waves, 1);
         CK(cudaEventRecord(w.ev_comp[rw], w.s_comp));
     } else {
         if (ov) {
@@ -727,8 +804,8 @@ static int run_wave(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry& b
             part.t_gather.push_back(tg);
         }
         CK(cudaEventRecord(w.ev_comp[rw], s_g));
-        p->stats.gather_launches++;
-        p->stats.gather_bytes += 2 * wt * cx.R;
+        STAT_ADD(p, gather_launches, 1);
+        STAT_ADD(p, gather_bytes, 2 * wt * cx.R);
     }
 
     // copy-out stream (streaming parts): D2H of the ordered window of this wave
@@ -738,7 +815,7 @@ static int run_wave(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry& b
         if (!cx.full_window) {
             CK(cudaStreamWaitEvent(w.s_out, w.ev_comp[rw], 0));
             CK(cudaMemcpyAsync((uint8_t*)st.out + wave_first * cx.R, w.d_out[half], wt * cx.R, cudaMemcpyDeviceToHost, w.s_out));
-            p->stats.d2h_bytes += wt * cx.R;
+            STAT_ADD(p, d2h_bytes, wt * cx.R);
             CK(cudaEventRecord(w.ev_out[half], w.s_out));
             CK(cudaEventRecord(wd, w.s_out));
         } else {
@@ -746,7 +823,7 @@ static int run_wave(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry& b
         }
         part.wave_done.push_back(wd);
     }
-    st.n_waves++;
+    __atomic_fetch_add(&st.n_waves, 1u, __ATOMIC_RELAXED);
     return FBR_OK;
 }
 
@@ -759,7 +836,7 @@ static int finish_round(fbr_pool* p, SeqState& st, SeqPart& part, bool copy_wind
     CK(cudaStreamWaitEvent(w.s_out, w.ev_comp[last_rw], 0));
     if (copy_window && cx.full_window && !cx.out_dev && !cx.keep_on_device && part.count) {
         CK(cudaMemcpyAsync((uint8_t*)st.out + part.first * cx.R, cx.window_base, part.count * cx.R, cudaMemcpyDeviceToHost, w.s_out));
-        p->stats.d2h_bytes += part.count * cx.R;
+        STAT_ADD(p, d2h_bytes, part.count * cx.R);
     }
     CK(cudaMemcpyAsync(&w.h_ctrl[slot], &w.d_ctrl[slot], sizeof(SeqCtrl), cudaMemcpyDeviceToHost, w.s_out));
     if (cx.resilient && part.lost_cap)
@@ -806,7 +883,7 @@ static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry
         } else {
             CK(cudaMallocAsync(&part.d_shared_tmp, d.shared_bytes, w.s_in));
             CK(cudaMemcpyAsync(part.d_shared_tmp, d.shared, d.shared_bytes, cudaMemcpyHostToDevice, w.s_in));
-            p->stats.h2d_bytes += d.shared_bytes;
+            STAT_ADD(p, h2d_bytes, d.shared_bytes);
             cx.d_shared = (const uint8_t*)part.d_shared_tmp;
         }
     }
@@ -827,7 +904,7 @@ static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry
         if (abytes)
             CK(cudaMemcpyAsync((uint8_t*)part.d_args_full + part.first * (uint64_t)d.arg_stride,
                                (const uint8_t*)d.args + part.first * (uint64_t)d.arg_stride, abytes, cudaMemcpyHostToDevice, w.s_in));
-        p->stats.h2d_bytes += abytes;
+        STAT_ADD(p, h2d_bytes, abytes);
         cx.args_full = (const uint8_t*)part.d_args_full;
     }
 
@@ -1130,7 +1207,7 @@ int fbr_internal_preload(int device) {
     cudaFuncGetAttributes(&at, (const void*)gather_ordered_kernel);
     cudaFuncGetAttributes(&at, (const void*)gather_rows_kernel);
     cudaFuncGetAttributes(&at, (const void*)gather_bulk_kernel);
-    cudaFuncGetAttributes(&at, (const void*)dispatch_payload_map_tma_kernel);
+    cudaFuncGetAttributes(&at, (const void*)dispatch_payload_map_tma_kernel<3, 2>);
     cudaFuncGetAttributes(&at, (const void*)payload_fill_kernel);
     cudaGetLastError();
     return FBR_OK;
@@ -1268,25 +1345,33 @@ int fbr_pool_create(int n_workers, const int* device_ids, uint64_t ring_bytes, u
             return rc;
         }
     }
-    // Peer access between all workers: lets one map keep its arguments / ordered output resident on
-    // worker 0 while every worker's dispatch kernel loads its block and its gather kernel stores its
-    // units straight over NVLink (scatter + gather fused into the kernels, no separate collective).
-    if (n_workers > 1) {
-        p->peer_ok = true;
-        for (int i = 0; i < n_workers && p->peer_ok; ++i)
-            for (int j = 0; j < n_workers; ++j) {
-                if (i == j) continue;
-                int can = 0;
-                cudaDeviceCanAccessPeer(&can, p->workers[i].device, p->workers[j].device);
-                if (!can) { p->peer_ok = false; break; }
-                cudaSetDevice(p->workers[i].device);
-                cudaError_t e = cudaDeviceEnablePeerAccess(p->workers[j].device, 0);
-                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) p->peer_ok = false;
-                cudaGetLastError();
-            }
-    }
+    // Peer access (NVLink P2P) is switched on by the first map that needs it (ensure_peer_access): contexts
+    // with peer mappings between them share their fate -- a kernel fault on one device takes the peers' contexts
+    // down with it -- so a pool that only runs host-resident maps keeps its workers' fault domains separate.
     *out = p.release();
     return FBR_OK;
+}
+
+// Peer access between all workers: lets one map keep its arguments / ordered output resident on worker 0
+// while every worker's dispatch kernel loads its block from there and stores its results there, straight
+// over NVLink (scatter + gather fused into the kernel, no separate collective).
+static bool ensure_peer_access(fbr_pool* p) {
+    if (p->peer_checked) return p->peer_ok;
+    p->peer_checked = true;
+    const int n = (int)p->workers.size();
+    p->peer_ok = n > 1;
+    for (int i = 0; i < n && p->peer_ok; ++i)
+        for (int j = 0; j < n; ++j) {
+            if (i == j) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, p->workers[i].device, p->workers[j].device);
+            if (!can) { p->peer_ok = false; break; }
+            cudaSetDevice(p->workers[i].device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(p->workers[j].device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) p->peer_ok = false;
+            cudaGetLastError();
+        }
+    return p->peer_ok;
 }
 
 int fbr_pool_n_workers(fbr_pool_t* p, int* n) {
@@ -1333,6 +1418,7 @@ int fbr_pool_destroy(fbr_pool_t* p) {
     if (!p) return FBR_OK;
     {
         std::lock_guard<std::mutex> g(p->mu);
+        p->submitters.clear();          // joins the submit threads
         for (auto& kv : p->seqs) free_seq(p, *kv.second);
         p->seqs.clear();
         for (auto& kv : p->shared)
@@ -1391,7 +1477,7 @@ int fbr_map_submit(fbr_pool_t* p, const fbr_map_desc_t* d, uint64_t* seq_out) {
     if (!body_of(d->func_id)) return fail(FBR_EINVAL, "bad func_id %d", d->func_id);
     const BodyEntry& body = *body_of(d->func_id);
     const bool dev_mode = (d->flags & (FBR_ARGS_DEVICE | FBR_OUT_DEVICE)) != 0;
-    if (dev_mode && p->workers.size() != 1 && !p->peer_ok)
+    if (dev_mode && p->workers.size() != 1 && !ensure_peer_access(p))
         return fail(FBR_EINVAL, "device-resident args/out on a multi-worker pool need peer access between all its GPUs");
     if (d->arg_stride == 0) {
         if (!(body.flags & FBR_BODY_INDEX_ARG))
@@ -1453,9 +1539,27 @@ int fbr_map_submit(fbr_pool_t* p, const fbr_map_desc_t* d, uint64_t* seq_out) {
             st->own_out = true;
         }
         int failed_worker = -1, rc = FBR_OK;
-        for (auto& part : st->parts) {
-            rc = submit_part(p, *st, part, body);
-            if (rc != FBR_OK) { failed_worker = part.worker; break; }
+        static const bool serial = getenv("FBR_SERIAL_SUBMIT") && atoi(getenv("FBR_SERIAL_SUBMIT")) != 0;
+        if (st->parts.size() > 1 && !serial) {
+            // one submit thread per worker (see SubmitThread); this thread holds the pool lock meanwhile
+            if (p->submitters.size() < p->workers.size()) p->submitters.resize(p->workers.size());
+            SeqState* stp = st.get();
+            for (auto& part : st->parts) {
+                auto& sub = p->submitters[part.worker];
+                if (!sub) sub.reset(new SubmitThread());
+                SeqPart* pp = &part;
+                sub->post([p, stp, pp, &body] { return submit_part(p, *stp, *pp, body); });
+            }
+            for (auto& part : st->parts) {
+                std::string msg;
+                const int r = p->submitters[part.worker]->wait(&msg);
+                if (r != FBR_OK && rc == FBR_OK) { rc = r; failed_worker = part.worker; g_err = msg; }
+            }
+        } else {
+            for (auto& part : st->parts) {
+                rc = submit_part(p, *st, part, body);
+                if (rc != FBR_OK) { failed_worker = part.worker; break; }
+            }
         }
         if (rc == FBR_OK) {
             p->stats.tasks_submitted += d->n_tasks;

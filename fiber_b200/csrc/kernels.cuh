@@ -806,13 +806,17 @@ __global__ void __launch_bounds__(32) gather_bulk_kernel(const GatherParams gp, 
 // Payload bytes cross registers only between two shared-memory stages; global traffic is TMA only.
 // ================================================================================================
 namespace tma_map {
-constexpr int kInStages = 3, kOutStages = 2;
 constexpr uint32_t kMapChunk = 16384;
 constexpr int kConsumers = 128;
 struct ChunkDesc { uint8_t* dst; uint32_t bytes; uint32_t tbase; };
-constexpr size_t kSmemBytes = (size_t)(kInStages + kOutStages) * kMapChunk;
+constexpr size_t smem_bytes(int in_stages, int out_stages) { return (size_t)(in_stages + out_stages) * kMapChunk; }
+constexpr size_t kSmemBytes = smem_bytes(3, 2);      // the default instantiation: 80 KB, two CTAs per SM
 }  // namespace tma_map
 
+// <3 IN, 2 OUT> stages, 2 CTAs/SM: local HBM (96 KB of loads in flight per SM).  <6, 3>, 1 CTA/SM: the same bytes
+// in flight from ONE producer per SM -- for records that live in a peer GPU's memory (NVLink round trips are ~4x
+// longer and the link prefers fewer, deeper request streams).
+template <int kInStages, int kOutStages>
 __global__ void __launch_bounds__(160) dispatch_payload_map_tma_kernel(const WaveParams wp) {
     using namespace bulk;
     using namespace tma_map;

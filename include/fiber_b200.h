@@ -348,6 +348,8 @@ int fbr_comm_scatter(fbr_comm_t* comm, const void* send_on_root, void* recv, uin
 int fbr_comm_allreduce(fbr_comm_t* comm, const void* send, void* recv, uint64_t count, int dtype, int op);
 int fbr_comm_allreduce_timed(fbr_comm_t* comm, void* buf, uint64_t count, int dtype, int op, int iters, float* ms_per_call);
 int fbr_comm_allreduce_i64(fbr_comm_t* comm, int64_t* value);       /* host scalar in, global sum out (the pi count) */
+int fbr_comm_allreduce_i64_begin(fbr_comm_t* comm, int64_t value);  /* the same, split: enqueue now ...               */
+int fbr_comm_allreduce_i64_end(fbr_comm_t* comm, int64_t* sum);     /* ... collect later (overlaps the next map)      */
 int fbr_comm_device_alloc(fbr_comm_t* comm, uint64_t bytes, void** dptr);
 int fbr_comm_device_free(fbr_comm_t* comm, void* dptr);
 int fbr_comm_memcpy_h2d(fbr_comm_t* comm, void* dptr, const void* src, uint64_t bytes);
