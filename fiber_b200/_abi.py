@@ -71,7 +71,8 @@ class MapDesc(ctypes.Structure):
                 ("chunksize", ctypes.c_uint32), ("arg_stride", ctypes.c_uint32), ("args", ctypes.c_void_p),
                 ("index_start", ctypes.c_int64), ("index_step", ctypes.c_int64),
                 ("shared", ctypes.c_void_p), ("shared_bytes", ctypes.c_uint64), ("out", ctypes.c_void_p),
-                ("task_index_base", ctypes.c_uint64), ("shuffle_seed", ctypes.c_uint64), ("n_items", ctypes.c_uint64)]
+                ("task_index_base", ctypes.c_uint64), ("shuffle_seed", ctypes.c_uint64), ("n_items", ctypes.c_uint64),
+                ("attempt", ctypes.c_uint32), ("pad", ctypes.c_uint32)]
 
 
 class Plan(ctypes.Structure):
@@ -95,7 +96,7 @@ class Stats(ctypes.Structure):
                 ("dispatch_ms", ctypes.c_double), ("gather_ms", ctypes.c_double),
                 ("gather_bytes", ctypes.c_uint64), ("dispatch_bytes", ctypes.c_uint64),
                 ("units_redispatched", ctypes.c_uint64), ("records_copied", ctypes.c_uint64),
-                ("direct_waves", ctypes.c_uint64), ("workers_lost", ctypes.c_uint64)]
+                ("direct_waves", ctypes.c_uint64), ("peer_push_bytes", ctypes.c_uint64), ("workers_lost", ctypes.c_uint64)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}

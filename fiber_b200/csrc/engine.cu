@@ -253,6 +253,9 @@ struct Worker {
     cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
     cudaStream_t s_gath = nullptr;         // higher-priority stream for gathers that overlap the next dispatch
     bool prev_wave_overlap = false;        // the previous wave used only its half of the ring
+    cudaStream_t s_push = nullptr;         // a stream of the ROOT worker's device: its copy engine pushes this worker's argument waves
+    cudaEvent_t ev_push[kRecWindows] = {}; // ... and these (root-device) events say when a pushed wave has landed
+    int push_root_device = -1;
     uint32_t gath_hist = 0;                // bit k: wave wno-1-k ran its gather on s_gath (its ev_comp is not ordered by s_comp)
     TaskRecord* h_records = nullptr;   // pinned task ring: kRecWindows x kRecCapacity
     TaskRecord* d_records = nullptr;   // device mirror
@@ -287,6 +290,8 @@ struct PartCtx {                          // constants of one worker's block of 
     uint32_t unit = 0, slot_stride = 0, R = 0, sum_kind = 0;
     bool args_dev = false, out_dev = false, full_window = false, host_args = false, resilient = false, keep_on_device = false;
     bool overlap = false;                 // gather(w) on s_gath concurrently with dispatch(w+1); ring used in halves
+    bool peer_push = false;               // arguments live on worker 0 (another GPU): worker 0's copy engine PUSHES each wave's
+                                          // records into this worker's staging halves over NVLink (host_args machinery)
     bool direct = false;                  // contiguous, unshuffled, non-resilient block: the dispatch kernel stores every
                                           // unit at its final index (no ring, no task records, no gather launch)
     const uint8_t* d_shared = nullptr;
@@ -557,6 +562,15 @@ static void worker_destroy(Worker& w) {
     if (w.s_comp) cudaStreamSynchronize(w.s_comp);
     if (w.s_out) cudaStreamSynchronize(w.s_out);
     if (w.s_gath) { cudaStreamSynchronize(w.s_gath); cudaStreamDestroy(w.s_gath); }
+    if (w.s_push) {                        // lives on the root worker's device
+        cudaSetDevice(w.push_root_device);
+        cudaStreamSynchronize(w.s_push);
+        cudaStreamDestroy(w.s_push);
+        for (int i = 0; i < kRecWindows; ++i) cudaEventDestroy(w.ev_push[i]);
+        cudaGetLastError();
+        cudaSetDevice(w.device);
+        w.s_push = nullptr;
+    }
     if (w.s_in) cudaStreamDestroy(w.s_in);
     if (w.s_comp) cudaStreamDestroy(w.s_comp);
     if (w.s_out) cudaStreamDestroy(w.s_out);
@@ -649,16 +663,35 @@ static int run_wave(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry& b
         STAT_ADD(p, records_copied, n_units);
     }
     const uint8_t* wave_args = cx.args_full;
-    if (cx.host_args) {   // streaming host arguments (contiguous waves only)
+    bool pushed = false;
+    if (cx.host_args) {   // streaming arguments (contiguous waves only): from the host, or pushed by the root GPU
         uint64_t bytes = wt * d.arg_stride;
         if (cx.args_limit_bytes) {   // the last task of the map may cover fewer argument items than a full record
             const uint64_t start = wave_first * (uint64_t)d.arg_stride;
             bytes = start >= cx.args_limit_bytes ? 0 : std::min(bytes, cx.args_limit_bytes - start);
         }
-        if (bytes)
-            CK(cudaMemcpyAsync(w.d_args[half], (const uint8_t*)d.args + wave_first * (uint64_t)d.arg_stride, bytes,
-                               cudaMemcpyHostToDevice, w.s_in));
-        STAT_ADD(p, h2d_bytes, bytes);
+        const uint8_t* src = (const uint8_t*)d.args + wave_first * (uint64_t)d.arg_stride;
+        if (cx.peer_push) {
+            // The copy runs on a stream of the ROOT device, so the root's copy engine WRITES the wave into this
+            // worker's staging half (posted NVLink writes, root TX), while this worker's kernels store their results
+            // into the root's output (posted writes, root RX): both directions of the root's links carry payload at
+            // the same time and neither carries read requests.  (Peer LOADS + peer stores from one kernel reach
+            // 504 GB/s each way)
+            if (bytes) {
+                CK(cudaSetDevice(w.push_root_device));
+                cudaError_t e = cudaStreamWaitEvent(w.s_push, w.ev_comp[rw], 0);                 // device window free
+                if (e == cudaSuccess && wno >= 2) e = cudaStreamWaitEvent(w.s_push, w.ev_comp[(wno - 2) % kRecWindows], 0);   // staging half free
+                if (e == cudaSuccess) e = cudaMemcpyPeerAsync(w.d_args[half], w.device, src, w.push_root_device, bytes, w.s_push);
+                if (e == cudaSuccess) e = cudaEventRecord(w.ev_push[rw], w.s_push);
+                cudaSetDevice(w.device);
+                if (e != cudaSuccess) return fail(FBR_ECUDA, "peer push of wave %llu failed: %s", (unsigned long long)wno, cudaGetErrorString(e));
+                pushed = true;
+                STAT_ADD(p, peer_push_bytes, bytes);
+            }
+        } else {
+            if (bytes) CK(cudaMemcpyAsync(w.d_args[half], src, bytes, cudaMemcpyHostToDevice, w.s_in));
+            STAT_ADD(p, h2d_bytes, bytes);
+        }
         wave_args = w.d_args[half];
     }
     if (in_copies) CK(cudaEventRecord(w.ev_rec_h2d[rw], w.s_in));
@@ -671,6 +704,7 @@ static int run_wave(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry& b
     uint8_t* ring_base = ov ? w.d_ring + (size_t)half * (p->ring_bytes / 2) : w.d_ring;
     SlotHeader* hdr_base = ov ? w.d_headers + (size_t)half * kRecCapacity : w.d_headers;
     if (in_copies) CK(cudaStreamWaitEvent(w.s_comp, w.ev_rec_h2d[rw], 0));
+    if (pushed) CK(cudaStreamWaitEvent(w.s_comp, w.ev_push[rw], 0));
     // the ring region this dispatch writes must have been drained by the gather that last read it (gathers on
     // s_comp itself are ordered by the stream: only a gather that ran on s_gath needs the event)
     if ((w.gath_hist & 3u) || ov) {
@@ -860,6 +894,24 @@ static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry
     cx.keep_on_device = (d.flags & FBR_RESULTS_ON_DEVICE) != 0;
     cx.full_window = cx.out_dev || cx.resilient || cx.keep_on_device || (d.flags & FBR_FULL_WINDOW);
     cx.host_args = d.arg_stride != 0 && !cx.args_dev && !cx.resilient;
+    {
+        // device-resident arguments on worker 0, consumed by another worker: stream them through the staging halves,
+        // pushed wave by wave by the root's copy engine (FBR_PEER_PUSH=0: the kernel loads them over NVLink itself)
+        static const bool push_off = getenv("FBR_PEER_PUSH") && atoi(getenv("FBR_PEER_PUSH")) == 0;
+        if (cx.args_dev && d.arg_stride != 0 && part.worker != 0 && !cx.resilient && !push_off && !p->workers[0].dead) {
+            if (w.s_push == nullptr) {
+                const int root = p->workers[0].device;
+                CK(cudaSetDevice(root));
+                cudaError_t e = cudaStreamCreateWithFlags(&w.s_push, cudaStreamNonBlocking);
+                for (int i = 0; i < kRecWindows && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&w.ev_push[i], cudaEventDisableTiming);
+                cudaSetDevice(w.device);
+                if (e != cudaSuccess) return fail(FBR_ECUDA, "creating the push stream on device %d failed: %s", root, cudaGetErrorString(e));
+                w.push_root_device = root;
+            }
+            cx.peer_push = true;
+            cx.host_args = true;       // same wave / staging machinery as host-resident arguments
+        }
+    }
     const uint32_t cs = d.chunksize ? d.chunksize : 32u;
     cx.unit = pick_unit(body, cs, part.count, w.sm_count, p->ring_bytes);
     cx.slot_stride = (uint32_t)round_up((uint64_t)cx.unit * cx.R, 16);
@@ -891,7 +943,7 @@ static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry
     if (d.n_items && d.arg_stride && body.result_kind == FBR_RES_BITS8)
         cx.args_limit_bytes = d.n_items * (uint64_t)(d.arg_stride / 8);   // a byte-task's record is 8 items
     // arguments that stay device-resident for the whole map
-    if (cx.args_dev) {
+    if (cx.args_dev && !cx.peer_push) {
         cx.args_full = (const uint8_t*)d.args;
     } else if (cx.resilient && d.arg_stride) {
         // lost units may be re-dispatched at any time: keep every argument record on the device
@@ -974,9 +1026,18 @@ static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry
         cx.sum_kind = 1;   // the dispatch kernel folds sum(results) while they are in registers
     }
 
+    // Tapered tail: the D2H of the LAST wave is the one copy no kernel overlaps, so the last waves of a block whose
+    // results stream to the host are cut in halves (down to ~256 KB of results) -- the exposed copy shrinks from a
+    // full wave to the smallest one.  (FBR_TAPER=0 switches it off.)
+    static const bool taper_on = !(getenv("FBR_TAPER") && atoi(getenv("FBR_TAPER")) == 0);
+    const bool taper = taper_on && !cx.full_window && !cx.host_args;
+    const uint64_t min_tail_tasks = round_up(std::max<uint64_t>(1, (256ull << 10) / std::max<uint32_t>(1, R)), unit);
     uint64_t done_tasks = 0;
     while (done_tasks < part.count) {
-        const uint64_t wt = std::min<uint64_t>(cx.wave_tasks_cap, part.count - done_tasks);
+        uint64_t wt = std::min<uint64_t>(cx.wave_tasks_cap, part.count - done_tasks);
+        const uint64_t left = part.count - done_tasks;
+        if (taper && left <= 2 * cx.wave_tasks_cap && left > min_tail_tasks)
+            wt = std::min(left, std::max(min_tail_tasks, round_up(left / 2, unit)));
         const uint32_t n_units = (uint32_t)((wt + unit - 1) / unit);
         const uint64_t wno = w.wave_no++;
         const int rw = (int)(wno % kRecWindows);
@@ -1528,7 +1589,7 @@ int fbr_map_submit(fbr_pool_t* p, const fbr_map_desc_t* d, uint64_t* seq_out) {
         }
         // contiguous task blocks per live worker, cut on claim-unit boundaries (block partition ==
         // PUSH round-robin with chunk = block)
-        cut_blocks(p, body, *d, 0, d->n_tasks, live, 0, st->parts);
+        cut_blocks(p, body, *d, 0, d->n_tasks, live, d->attempt, st->parts);
         if (need_segment && live.size() > 1) {
             // several GPUs fill one segment: bind each worker's block to its GPU's NUMA node
             std::vector<NumaBlock> blocks;

@@ -425,7 +425,7 @@ class Pool:
 
     def __init__(self, processes=None, initializer=None, initargs=(), maxtasksperchild=None,
                  error_handling=False, *, devices=None, ring_bytes=0, timing=False, results="host", express=True,
-                 express_idle_us=2000, bind_cpu=False):
+                 express_idle_us=2000, bind_cpu=False, isolation="thread"):
         self._processes = processes if processes is not None else 1   # fiber/pool.py:894
         if self._processes < 1:
             raise ValueError("Number of processes must be at least 1")
@@ -455,6 +455,12 @@ class Pool:
         self._use_express = bool(express) and not self._error_handling
         self._express_idle_us = int(express_idle_us)
         self._express = None
+        if isolation not in ("thread", "process"):
+            raise ValueError("isolation must be 'thread' (workers are devices of this process) or 'process' (one worker process "
+                             "per GPU: the only fault domain CUDA offers -- see fiber_b200/procpool.py)")
+        self._isolation = isolation
+        self._proc = None                    # ProcessPool when isolation == "process"
+        self._attempt = 0                    # re-dispatch count stamped on submitted blocks (set by process-pool workers)
         self._bind_cpu = bool(bind_cpu)      # one process per GPU: keep pinned segments on the GPU's NUMA node
         self.bound_cpus = []
         self._state = RUN
@@ -472,6 +478,20 @@ class Pool:
 
     # -- workers (fiber/pool.py:1118-1137, 1405-1422) ---------------------------------------------
     def start_workers(self):
+        if self._isolation == "process":
+            if self._proc is None:
+                from .procpool import ProcessPool
+                lib = _abi.load()
+                n = ctypes.c_int(0)
+                _abi.check(lib.fbr_device_count(ctypes.byref(n)))            # counts devices, creates no context
+                if n.value == 0:
+                    raise _abi.EngineError(_abi.FBR_ENODEV, "no CUDA device visible; fiber_b200 has no CPU fallback")
+                devs = self._devices if self._devices is not None else list(range(n.value))
+                self._proc = ProcessPool(self._processes, devs, results="bytes" if not self._results_bits else "host",
+                                         redispatch=self._error_handling)
+            self._proc.start()
+            self._worker_handler_started = True
+            return
         if self._engine is None:
             lib = _abi.load()
             n = ctypes.c_int(0)
@@ -506,6 +526,8 @@ class Pool:
 
     def wait_until_workers_up(self):
         self.start_workers()
+        if self._proc is not None:
+            self._proc.wait_until_workers_up()
 
     @property
     def n_jobs(self):
@@ -579,6 +601,7 @@ class Pool:
             flags |= _abi.FBR_SHARED_HANDLE
         d.n_items = enc.n_items
         d.task_index_base = enc.task_index_base
+        d.attempt = self._attempt
         d.flags = flags
         seq = ctypes.c_uint64(0)
         if enc.n:
@@ -609,10 +632,23 @@ class Pool:
             iterable = list(iterable)
         spec = self._spec_of(func)
         self.lazy_start_workers(func)
+        if self._proc is not None:
+            return self._submit_proc(spec, "map", iterable, chunksize)
         enc = spec.encode_map(iterable)
         if self._results_bits and spec.name in registry.BITS_TWIN:
             return self._submit_bits(func, spec, enc, _abi.FBR_MAP, chunksize)
         return self._submit(func, enc, _abi.FBR_MAP, chunksize)
+
+    def _submit_proc(self, spec, kind, items, chunksize, single=False):
+        """Process-isolated workers: the map is cut into blocks that worker processes pull (procpool.py)."""
+        if not isinstance(items, (range, list, np.ndarray)):
+            items = list(items)
+        if kind == "map" and len(items):
+            spec.encode_map(items[:1] if not isinstance(items, range) else items)      # argument validation up front
+        twin = registry.BITS_TWIN.get(spec.name) if (self._results_bits and kind != "apply") else None
+        r = self._proc.submit(spec, twin, kind, items, chunksize, single)
+        self.sent_tasks += len(items)
+        return r
 
     def _submit_bits(self, func, spec, enc, kind, chunksize):
         """A bool needs one bit: the twin body evaluates 8 consecutive items (range() indices or argument
@@ -635,6 +671,8 @@ class Pool:
             iterable = list(iterable)
         spec = self._spec_of(func)
         self.lazy_start_workers(func)
+        if self._proc is not None:
+            return self._submit_proc(spec, "starmap", list(iterable), chunksize)
         enc = spec.encode_starmap(iterable)
         if self._results_bits and spec.name in registry.BITS_TWIN:
             return self._submit_bits(func, spec, enc, _abi.FBR_STARMAP, chunksize)
@@ -647,6 +685,8 @@ class Pool:
         self._check_running()
         spec = self._spec_of(func)
         self.lazy_start_workers(func)
+        if self._proc is not None:
+            return self._submit_proc(spec, "apply", [(tuple(args), dict(kwds))], 1, single=True)
         if self._use_express and spec.name in _Express.BODIES:
             # one task whose record fits the doorbell lane: no kernel launch / copy on the round trip
             rec = spec.pack_apply(args, kwds)
@@ -663,25 +703,33 @@ class Pool:
         return self.apply_async(func, args, kwds).get()
 
     def imap(self, func, iterable, chunksize=1):
-        return self.map_async(func, iterable, chunksize).iget_ordered()
+        r = self.map_async(func, iterable, chunksize)
+        return iter(r.get()) if self._proc is not None else r.iget_ordered()
 
     def imap_unordered(self, func, iterable, chunksize=1):
-        return self.map_async(func, iterable, chunksize).iget_unordered()
+        r = self.map_async(func, iterable, chunksize)
+        return iter(r.get()) if self._proc is not None else r.iget_unordered()
 
     # -- shutdown (fiber/pool.py:1332-1403) -----------------------------------------------------------
     def close(self):
         if self._state == RUN:
             self._state = CLOSE
+            if self._proc is not None:
+                self._proc.close()
             if self._engine is not None:
                 self._engine.lib.fbr_pool_close(self._engine.handle)
 
     def terminate(self):
         self._state = TERMINATE
+        if self._proc is not None:
+            self._proc.terminate()
         if self._engine is not None:
             self._engine.lib.fbr_pool_terminate(self._engine.handle)
 
     def join(self):
         assert self._state in (TERMINATE, CLOSE)
+        if self._proc is not None:
+            self._proc.join()
         if self._engine is not None:
             _abi.check(self._engine.lib.fbr_pool_join(self._engine.handle))
 
@@ -699,6 +747,8 @@ class Pool:
     def stats(self):
         """``fbr_pool_stats`` as a dict (extends the reference's sent_tasks/recv_tasks counters)."""
         self.start_workers()
+        if self._proc is not None:
+            return dict(self._proc.stats)
         s = _abi.Stats()
         _abi.check(self._engine.lib.fbr_pool_stats(self._engine.handle, ctypes.byref(s)))
         d = s.as_dict()

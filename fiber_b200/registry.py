@@ -47,9 +47,18 @@ def device_body(name, source=None, entry="fbr_body_entry", args="i64", **meta):
     return decorator
 
 
+_MODULES = {}   # body name -> (module path, entry, argument layout) of bodies registered from their own module
+
+
+def module_of(name):
+    """Where an out-of-tree body came from (worker processes of a process-isolated pool register it themselves)."""
+    return _MODULES.get(name)
+
+
 def register_module(name, module_path, entry="fbr_body_entry", args="i64"):
     """``fbr_register_body`` + the host-side encoder for the body's argument records."""
     import ctypes
+    _MODULES[name] = (str(module_path), entry, args)
     L = _abi.load()
     fid = ctypes.c_int(-1)
     _abi.check(L.fbr_register_body(name.encode(), str(module_path).encode(), entry.encode(), ctypes.byref(fid)))

@@ -172,6 +172,10 @@ typedef struct fbr_map_desc {
     uint64_t shuffle_seed;
     uint64_t n_items;        /* FBR_RES_BITS8 bodies with explicit arguments: number of argument items of the
                                 whole map (the last task may cover fewer than 8); 0 = 8 * n_tasks */
+    uint32_t attempt;        /* how many times this block of tasks has been dispatched before (a resilient pool that
+                                re-queues a dead worker's chunk, fiber/pool.py:1635-1654, passes attempt + 1); bodies
+                                see it as their `attempt` argument */
+    uint32_t pad;
 } fbr_map_desc_t;
 
 int fbr_map_submit(fbr_pool_t* pool, const fbr_map_desc_t* desc, uint64_t* seq);
@@ -256,6 +260,8 @@ typedef struct fbr_stats {
     uint64_t units_redispatched;        /* lost units re-queued by resilient maps (pending-table resubmits) */
     uint64_t records_copied;            /* task records written to the pinned ring and copied to the device */
     uint64_t direct_waves;              /* waves whose dispatch kernel stored at the final index (no gather) */
+    uint64_t peer_push_bytes;           /* argument bytes pushed from worker 0's memory into other workers' staging by
+                                           worker 0's copy engine (root-resident maps over NVLink) */
     uint64_t workers_lost;              /* workers retired because their CUDA context died (sticky error); maps with
                                            FBR_RESILIENT had their blocks re-dispatched to the surviving workers */
 } fbr_stats_t;

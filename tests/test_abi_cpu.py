@@ -41,7 +41,7 @@ def test_header_constants_match_binding():
         m = re.search(r"%s = (-\d+)" % name, header)
         assert m and int(m.group(1)) == getattr(_abi, name), name
     # struct sizes the C side static_asserts / the binding mirrors
-    assert ctypes.sizeof(_abi.MapDesc) == 96 and ctypes.sizeof(_abi.Result) == 80 and ctypes.sizeof(_abi.Stats) == 128 and ctypes.sizeof(_abi.BodyInfo) == 64
+    assert ctypes.sizeof(_abi.MapDesc) == 104 and ctypes.sizeof(_abi.Result) == 80 and ctypes.sizeof(_abi.Stats) == 136 and ctypes.sizeof(_abi.BodyInfo) == 64
 
 
 def test_body_table():
