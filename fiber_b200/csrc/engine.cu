@@ -67,13 +67,13 @@ void SubmitThread_loop_impl(SubmitThread* t);
 // async copies, event records: ~50 us per part of 8 waves) run side by side instead of one after the other,
 // which is what an 8-GPU in-process pool needs to keep up with 0.25 ms kernels.
 struct SubmitThread {
-    std::thread th;
     std::mutex mu;
     std::condition_variable cv;
     std::function<int()> job;
     bool pending = false, finished = false, quit = false;
     int rc = 0;
     std::string err;
+    std::thread th;             // declared LAST: it starts running in the constructor and uses every member above
     SubmitThread() : th([this] { loop(); }) {}
     ~SubmitThread() {
         { std::lock_guard<std::mutex> g(mu); quit = true; }
@@ -290,6 +290,8 @@ struct PartCtx {                          // constants of one worker's block of 
     uint32_t unit = 0, slot_stride = 0, R = 0, sum_kind = 0;
     bool args_dev = false, out_dev = false, full_window = false, host_args = false, resilient = false, keep_on_device = false;
     bool overlap = false;                 // gather(w) on s_gath concurrently with dispatch(w+1); ring used in halves
+    bool peer_out = false;                // the ordered output lives on worker 0 (another GPU): results are computed into the local
+                                          // out-staging halves and PUSHED there by this worker's copy engine (the D2H machinery)
     bool peer_push = false;               // arguments live on worker 0 (another GPU): worker 0's copy engine PUSHES each wave's
                                           // records into this worker's staging halves over NVLink (host_args machinery)
     bool direct = false;                  // contiguous, unshuffled, non-resilient block: the dispatch kernel stores every
@@ -848,8 +850,13 @@ static int run_wave(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry& b
         CK(cudaEventCreateWithFlags(&wd, cudaEventDisableTiming));
         if (!cx.full_window) {
             CK(cudaStreamWaitEvent(w.s_out, w.ev_comp[rw], 0));
-            CK(cudaMemcpyAsync((uint8_t*)st.out + wave_first * cx.R, w.d_out[half], wt * cx.R, cudaMemcpyDeviceToHost, w.s_out));
-            STAT_ADD(p, d2h_bytes, wt * cx.R);
+            if (cx.peer_out) {      // this worker's copy engine writes the wave into the root's ordered output (posted NVLink writes)
+                CK(cudaMemcpyPeerAsync((uint8_t*)st.out + wave_first * cx.R, p->workers[0].device, w.d_out[half], w.device, wt * cx.R, w.s_out));
+                STAT_ADD(p, peer_push_bytes, wt * cx.R);
+            } else {
+                CK(cudaMemcpyAsync((uint8_t*)st.out + wave_first * cx.R, w.d_out[half], wt * cx.R, cudaMemcpyDeviceToHost, w.s_out));
+                STAT_ADD(p, d2h_bytes, wt * cx.R);
+            }
             CK(cudaEventRecord(w.ev_out[half], w.s_out));
             CK(cudaEventRecord(wd, w.s_out));
         } else {
@@ -892,7 +899,15 @@ static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry
     cx.args_dev = (d.flags & FBR_ARGS_DEVICE) != 0;
     cx.out_dev = (d.flags & FBR_OUT_DEVICE) != 0;
     cx.keep_on_device = (d.flags & FBR_RESULTS_ON_DEVICE) != 0;
-    cx.full_window = cx.out_dev || cx.resilient || cx.keep_on_device || (d.flags & FBR_FULL_WINDOW);
+    {
+        // Output resident on worker 0, computed by another worker: kernels storing over NVLink top out near 510 GB/s
+        // (TMA bulk or register stores alike), a copy engine pushes at the peer-copy rate (~770 GB/s).  So the block is
+        // computed into the local out-staging halves and each wave is pushed to the root by this worker's copy engine,
+        // overlapping the next wave's kernel (FBR_PEER_OUT=0: the kernel stores into the root's memory itself).
+        static const bool out_off = getenv("FBR_PEER_OUT") && atoi(getenv("FBR_PEER_OUT")) == 0;
+        cx.peer_out = cx.out_dev && part.worker != 0 && !cx.resilient && !out_off && !(d.flags & FBR_FULL_WINDOW);
+    }
+    cx.full_window = (cx.out_dev && !cx.peer_out) || cx.resilient || cx.keep_on_device || (d.flags & FBR_FULL_WINDOW);
     cx.host_args = d.arg_stride != 0 && !cx.args_dev && !cx.resilient;
     {
         // device-resident arguments on worker 0, consumed by another worker: stream them through the staging halves,
@@ -1026,16 +1041,25 @@ static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry
         cx.sum_kind = 1;   // the dispatch kernel folds sum(results) while they are in registers
     }
 
-    // Tapered tail: the D2H of the LAST wave is the one copy no kernel overlaps, so the last waves of a block whose
-    // results stream to the host are cut in halves (down to ~256 KB of results) -- the exposed copy shrinks from a
-    // full wave to the smallest one.  (FBR_TAPER=0 switches it off.)
-    static const bool taper_on = !(getenv("FBR_TAPER") && atoi(getenv("FBR_TAPER")) == 0);
-    const bool taper = taper_on && !cx.full_window && !cx.host_args;
+    // Wave schedule of a block whose results stream out (host segment or the root GPU): the chain of copy-outs is the
+    // critical path when a wave's copy takes longer than its kernel (12.5 MB of bit-packed pi results: 38 us per
+    // 1.56 MB D2H against 31 us of kernel), so the FIRST copy should start as early as possible: the block opens with
+    // a quarter-size and a half-size wave (FBR_RAMP=0: equal waves).  Measured and dropped: halving the LAST waves to
+    // shrink the exposed tail copy (FBR_TAPER=1) -- every extra wave costs ~9 us of chain latency, more than it saves
+    // (0.375 vs 0.357 ms per 1e8-task map).
+    static const bool taper_on = getenv("FBR_TAPER") && atoi(getenv("FBR_TAPER")) != 0;
+    static const bool ramp_on = !(getenv("FBR_RAMP") && atoi(getenv("FBR_RAMP")) == 0);
+    const bool streaming_out = !cx.full_window && !cx.host_args;
+    const bool taper = taper_on && streaming_out;
+    const bool ramp = ramp_on && streaming_out && part.count > 4 * cx.wave_tasks_cap;
     const uint64_t min_tail_tasks = round_up(std::max<uint64_t>(1, (256ull << 10) / std::max<uint32_t>(1, R)), unit);
     uint64_t done_tasks = 0;
+    uint32_t wave_idx = 0;
     while (done_tasks < part.count) {
         uint64_t wt = std::min<uint64_t>(cx.wave_tasks_cap, part.count - done_tasks);
         const uint64_t left = part.count - done_tasks;
+        if (ramp && wave_idx < 2) wt = std::min(left, round_up(cx.wave_tasks_cap >> (2 - wave_idx), unit));
+        ++wave_idx;
         if (taper && left <= 2 * cx.wave_tasks_cap && left > min_tail_tasks)
             wt = std::min(left, std::max(min_tail_tasks, round_up(left / 2, unit)));
         const uint32_t n_units = (uint32_t)((wt + unit - 1) / unit);
