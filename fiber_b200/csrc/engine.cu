@@ -251,9 +251,12 @@ struct Worker {
     int numa_node = -1;                    // host NUMA node the GPU hangs off (-1 unknown)
     int sm_count = 0;
     cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
+    cudaStream_t s_out2 = nullptr;         // copy-outs alternate between s_out and s_out2 (by staging half): the set-up of one copy
+                                           // (~8 us per cudaMemcpyAsync on the DMA engine) overlaps the transfer of the other
     cudaStream_t s_gath = nullptr;         // higher-priority stream for gathers that overlap the next dispatch
     bool prev_wave_overlap = false;        // the previous wave used only its half of the ring
     cudaStream_t s_push = nullptr;         // a stream of the ROOT worker's device: its copy engine pushes this worker's argument waves
+    cudaStream_t s_push2 = nullptr;        // (waves alternate between the two, like the copy-outs)
     cudaEvent_t ev_push[kRecWindows] = {}; // ... and these (root-device) events say when a pushed wave has landed
     int push_root_device = -1;
     uint32_t gath_hist = 0;                // bit k: wave wno-1-k ran its gather on s_gath (its ev_comp is not ordered by s_comp)
@@ -511,6 +514,7 @@ static int worker_init(fbr_pool* p, Worker& w, int device) {
     CK(cudaStreamCreateWithFlags(&w.s_in, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&w.s_comp, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&w.s_out, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&w.s_out2, cudaStreamNonBlocking));
     {
         int lo_prio = 0, hi_prio = 0;
         CK(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
@@ -563,11 +567,13 @@ static void worker_destroy(Worker& w) {
     if (w.s_in) cudaStreamSynchronize(w.s_in);
     if (w.s_comp) cudaStreamSynchronize(w.s_comp);
     if (w.s_out) cudaStreamSynchronize(w.s_out);
+    if (w.s_out2) { cudaStreamSynchronize(w.s_out2); cudaStreamDestroy(w.s_out2); }
     if (w.s_gath) { cudaStreamSynchronize(w.s_gath); cudaStreamDestroy(w.s_gath); }
     if (w.s_push) {                        // lives on the root worker's device
         cudaSetDevice(w.push_root_device);
         cudaStreamSynchronize(w.s_push);
         cudaStreamDestroy(w.s_push);
+        if (w.s_push2) { cudaStreamSynchronize(w.s_push2); cudaStreamDestroy(w.s_push2); }
         for (int i = 0; i < kRecWindows; ++i) cudaEventDestroy(w.ev_push[i]);
         cudaGetLastError();
         cudaSetDevice(w.device);
@@ -681,10 +687,11 @@ static int run_wave(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry& b
             // 504 GB/s each way)
             if (bytes) {
                 CK(cudaSetDevice(w.push_root_device));
-                cudaError_t e = cudaStreamWaitEvent(w.s_push, w.ev_comp[rw], 0);                 // device window free
-                if (e == cudaSuccess && wno >= 2) e = cudaStreamWaitEvent(w.s_push, w.ev_comp[(wno - 2) % kRecWindows], 0);   // staging half free
-                if (e == cudaSuccess) e = cudaMemcpyPeerAsync(w.d_args[half], w.device, src, w.push_root_device, bytes, w.s_push);
-                if (e == cudaSuccess) e = cudaEventRecord(w.ev_push[rw], w.s_push);
+                cudaStream_t sp = half ? w.s_push2 : w.s_push;
+                cudaError_t e = cudaStreamWaitEvent(sp, w.ev_comp[rw], 0);                 // device window free
+                if (e == cudaSuccess && wno >= 2) e = cudaStreamWaitEvent(sp, w.ev_comp[(wno - 2) % kRecWindows], 0);   // staging half free
+                if (e == cudaSuccess) e = cudaMemcpyPeerAsync(w.d_args[half], w.device, src, w.push_root_device, bytes, sp);
+                if (e == cudaSuccess) e = cudaEventRecord(w.ev_push[rw], sp);
                 cudaSetDevice(w.device);
                 if (e != cudaSuccess) return fail(FBR_ECUDA, "peer push of wave %llu failed: %s", (unsigned long long)wno, cudaGetErrorString(e));
                 pushed = true;
@@ -849,16 +856,18 @@ static int run_wave(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry& b
         cudaEvent_t wd;
         CK(cudaEventCreateWithFlags(&wd, cudaEventDisableTiming));
         if (!cx.full_window) {
-            CK(cudaStreamWaitEvent(w.s_out, w.ev_comp[rw], 0));
+            static const bool one_out = getenv("FBR_ONE_OUT_STREAM") && atoi(getenv("FBR_ONE_OUT_STREAM")) != 0;
+            cudaStream_t so = (half && !one_out) ? w.s_out2 : w.s_out;
+            CK(cudaStreamWaitEvent(so, w.ev_comp[rw], 0));
             if (cx.peer_out) {      // this worker's copy engine writes the wave into the root's ordered output (posted NVLink writes)
-                CK(cudaMemcpyPeerAsync((uint8_t*)st.out + wave_first * cx.R, p->workers[0].device, w.d_out[half], w.device, wt * cx.R, w.s_out));
+                CK(cudaMemcpyPeerAsync((uint8_t*)st.out + wave_first * cx.R, p->workers[0].device, w.d_out[half], w.device, wt * cx.R, so));
                 STAT_ADD(p, peer_push_bytes, wt * cx.R);
             } else {
-                CK(cudaMemcpyAsync((uint8_t*)st.out + wave_first * cx.R, w.d_out[half], wt * cx.R, cudaMemcpyDeviceToHost, w.s_out));
+                CK(cudaMemcpyAsync((uint8_t*)st.out + wave_first * cx.R, w.d_out[half], wt * cx.R, cudaMemcpyDeviceToHost, so));
                 STAT_ADD(p, d2h_bytes, wt * cx.R);
             }
-            CK(cudaEventRecord(w.ev_out[half], w.s_out));
-            CK(cudaEventRecord(wd, w.s_out));
+            CK(cudaEventRecord(w.ev_out[half], so));
+            CK(cudaEventRecord(wd, so));
         } else {
             CK(cudaEventRecord(wd, direct ? w.s_comp : s_g));
         }
@@ -875,6 +884,8 @@ static int finish_round(fbr_pool* p, SeqState& st, SeqPart& part, bool copy_wind
     const int slot = part.ctrl_slot;
     const int last_rw = (int)((w.wave_no - 1) % kRecWindows);
     CK(cudaStreamWaitEvent(w.s_out, w.ev_comp[last_rw], 0));
+    CK(cudaStreamWaitEvent(w.s_out, w.ev_out[0], 0));      // copy-outs issued on either out stream are complete
+    CK(cudaStreamWaitEvent(w.s_out, w.ev_out[1], 0));
     if (copy_window && cx.full_window && !cx.out_dev && !cx.keep_on_device && part.count) {
         CK(cudaMemcpyAsync((uint8_t*)st.out + part.first * cx.R, cx.window_base, part.count * cx.R, cudaMemcpyDeviceToHost, w.s_out));
         STAT_ADD(p, d2h_bytes, part.count * cx.R);
@@ -918,6 +929,7 @@ static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry
                 const int root = p->workers[0].device;
                 CK(cudaSetDevice(root));
                 cudaError_t e = cudaStreamCreateWithFlags(&w.s_push, cudaStreamNonBlocking);
+                if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w.s_push2, cudaStreamNonBlocking);
                 for (int i = 0; i < kRecWindows && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&w.ev_push[i], cudaEventDisableTiming);
                 cudaSetDevice(w.device);
                 if (e != cudaSuccess) return fail(FBR_ECUDA, "creating the push stream on device %d failed: %s", root, cudaGetErrorString(e));
@@ -1010,6 +1022,8 @@ static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry
         // 8 waves for ~100 MB maps, up to 64 for multi-GB ones (~64 MiB per wave): the first wave's
         // H2D and the last wave's D2H are the only copies nothing overlaps with
         uint64_t n_waves = std::min<uint64_t>(64, std::max<uint64_t>(8, part.count * bytes_per_task / (64ull << 20)));
+        // small outputs (bit-packed bools): per-copy set-up weighs more: T_kernel/n + n * 8 us is flattest at n = 5..6
+        if (body.result_kind == FBR_RES_BITS8 && !cx.host_args) n_waves = 6;
         if (const char* e = getenv("FBR_WAVES")) n_waves = std::max<uint64_t>(1, (uint64_t)atoll(e));                          // tuning knob
         const uint64_t share = round_up((part.count + n_waves - 1) / n_waves, unit);
         cx.wave_tasks_cap = std::min(cx.wave_tasks_cap, std::max(min_wave_tasks, share));
@@ -1043,12 +1057,12 @@ static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry
 
     // Wave schedule of a block whose results stream out (host segment or the root GPU): the chain of copy-outs is the
     // critical path when a wave's copy takes longer than its kernel (12.5 MB of bit-packed pi results: 38 us per
-    // 1.56 MB D2H against 31 us of kernel), so the FIRST copy should start as early as possible: the block opens with
-    // a quarter-size and a half-size wave (FBR_RAMP=0: equal waves).  Measured and dropped: halving the LAST waves to
-    // shrink the exposed tail copy (FBR_TAPER=1) -- every extra wave costs ~9 us of chain latency, more than it saves
-    // (0.375 vs 0.357 ms per 1e8-task map).
+    // 1.56 MB D2H -- 30 us of transfer + ~8 us of set-up -- against 31 us of kernel).  Equal waves are the default.
+    // Measured and dropped (each extra wave costs more chain latency than the schedule saves): opening the block with
+    // a quarter-size and a half-size wave so the first copy starts earlier (FBR_RAMP=1: 0.374 vs 0.358 ms per
+    // 1e8-task map), halving the LAST waves to shrink the exposed tail copy (FBR_TAPER=1: 0.375 vs 0.357 ms).
     static const bool taper_on = getenv("FBR_TAPER") && atoi(getenv("FBR_TAPER")) != 0;
-    static const bool ramp_on = !(getenv("FBR_RAMP") && atoi(getenv("FBR_RAMP")) == 0);
+    static const bool ramp_on = getenv("FBR_RAMP") && atoi(getenv("FBR_RAMP")) != 0;
     const bool streaming_out = !cx.full_window && !cx.host_args;
     const bool taper = taper_on && streaming_out;
     const bool ramp = ramp_on && streaming_out && part.count > 4 * cx.wave_tasks_cap;
@@ -1495,6 +1509,7 @@ int fbr_pool_join(fbr_pool_t* p) {
         CK(cudaStreamSynchronize(w.s_comp));
         CK(cudaStreamSynchronize(w.s_gath));
         CK(cudaStreamSynchronize(w.s_out));
+        CK(cudaStreamSynchronize(w.s_out2));
     }
     return FBR_OK;
 }
@@ -1606,9 +1621,23 @@ int fbr_map_submit(fbr_pool_t* p, const fbr_map_desc_t* d, uint64_t* seq_out) {
         st->out = d->out;
         st->desc = *d;
         const bool need_segment = !st->out && d->n_tasks && !(d->flags & FBR_RESULTS_ON_DEVICE);
+        // host allocations fail with the sticky error too once a context of this process has died: tell the two apart
+        auto died_meanwhile = [&]() {
+            bool any = false;
+            for (int wi : live) {
+                cudaError_t why = cudaSuccess;
+                if (worker_context_dead(p->workers[wi], &why)) { on_worker_death(p, wi, why); any = true; }
+            }
+            return any;
+        };
         if (need_segment && live.size() == 1) {
             int rc = pinned_acquire(p, d->n_tasks * body.result_bytes, &st->out);
-            if (rc != FBR_OK) return rc;
+            if (rc != FBR_OK) {
+                const std::string msg = g_err;
+                if (died_meanwhile()) continue;
+                g_err = msg;
+                return rc;
+            }
             st->own_out = true;
         }
         // contiguous task blocks per live worker, cut on claim-unit boundaries (block partition ==
@@ -1620,7 +1649,12 @@ int fbr_map_submit(fbr_pool_t* p, const fbr_map_desc_t* d, uint64_t* seq_out) {
             for (auto& part : st->parts)
                 blocks.push_back({part.first * body.result_bytes, part.count * body.result_bytes, p->workers[part.worker].numa_node});
             int rc = numa_pinned_acquire(p, d->n_tasks * body.result_bytes, blocks, &st->out);
-            if (rc != FBR_OK) return rc;
+            if (rc != FBR_OK) {
+                const std::string msg = g_err;
+                if (died_meanwhile()) continue;
+                g_err = msg;
+                return rc;
+            }
             st->own_out = true;
         }
         int failed_worker = -1, rc = FBR_OK;
