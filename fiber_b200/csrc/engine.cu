@@ -251,8 +251,7 @@ struct Worker {
     int numa_node = -1;                    // host NUMA node the GPU hangs off (-1 unknown)
     int sm_count = 0;
     cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
-    cudaStream_t s_out2 = nullptr;         // copy-outs alternate between s_out and s_out2 (by staging half): the set-up of one copy
-                                           // (~8 us per cudaMemcpyAsync on the DMA engine) overlaps the transfer of the other
+    cudaStream_t s_out2 = nullptr;         // FBR_TWO_OUT_STREAMS=1: copy-outs alternate between s_out and s_out2 (by staging half)
     cudaStream_t s_gath = nullptr;         // higher-priority stream for gathers that overlap the next dispatch
     bool prev_wave_overlap = false;        // the previous wave used only its half of the ring
     cudaStream_t s_push = nullptr;         // a stream of the ROOT worker's device: its copy engine pushes this worker's argument waves
@@ -856,8 +855,10 @@ static int run_wave(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry& b
         cudaEvent_t wd;
         CK(cudaEventCreateWithFlags(&wd, cudaEventDisableTiming));
         if (!cx.full_window) {
-            static const bool one_out = getenv("FBR_ONE_OUT_STREAM") && atoi(getenv("FBR_ONE_OUT_STREAM")) != 0;
-            cudaStream_t so = (half && !one_out) ? w.s_out2 : w.s_out;
+            // one copy-out stream by default; alternating two (FBR_TWO_OUT_STREAMS=1) was measured and did not pay:
+            // 0.362 vs 0.347 ms per 1e8-task map over PCIe, 3.40 vs 3.41 ms for the NVLink push of 2 GB
+            static const bool two_out = getenv("FBR_TWO_OUT_STREAMS") && atoi(getenv("FBR_TWO_OUT_STREAMS")) != 0;
+            cudaStream_t so = (half && two_out) ? w.s_out2 : w.s_out;
             CK(cudaStreamWaitEvent(so, w.ev_comp[rw], 0));
             if (cx.peer_out) {      // this worker's copy engine writes the wave into the root's ordered output (posted NVLink writes)
                 CK(cudaMemcpyPeerAsync((uint8_t*)st.out + wave_first * cx.R, p->workers[0].device, w.d_out[half], w.device, wt * cx.R, so));
