@@ -24,7 +24,7 @@ FBR_POOL_TIMING, FBR_POOL_OVERLAP = 0x1, 0x2
 # map flags
 FBR_MAP, FBR_STARMAP, FBR_APPLY = 0x0, 0x1, 0x2
 FBR_ARGS_DEVICE, FBR_OUT_DEVICE, FBR_WANT_SUM, FBR_SHUFFLE, FBR_FULL_WINDOW, FBR_SHARED_HANDLE, FBR_RESILIENT, \
-    FBR_RESULTS_ON_DEVICE, FBR_VIA_RING = 0x10, 0x20, 0x40, 0x80, 0x100, 0x200, 0x400, 0x800, 0x1000
+    FBR_RESULTS_ON_DEVICE, FBR_VIA_RING, FBR_NO_ZERO_COPY = 0x10, 0x20, 0x40, 0x80, 0x100, 0x200, 0x400, 0x800, 0x1000, 0x2000
 # fbr_task_error
 FBR_TASK_OK, FBR_TASK_OVERFLOW, FBR_TASK_BADARG, FBR_TASK_FAULT = range(4)
 

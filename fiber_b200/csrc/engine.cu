@@ -292,6 +292,8 @@ struct PartCtx {                          // constants of one worker's block of 
     uint32_t unit = 0, slot_stride = 0, R = 0, sum_kind = 0;
     bool args_dev = false, out_dev = false, full_window = false, host_args = false, resilient = false, keep_on_device = false;
     bool overlap = false;                 // gather(w) on s_gath concurrently with dispatch(w+1); ring used in halves
+    bool zero_copy = false;               // small host-resident results: the dispatch kernel stores them straight into the pinned
+                                          // result segment over PCIe (no staging, no D2H copy, one wave)
     bool peer_out = false;                // the ordered output lives on worker 0 (another GPU): results are computed into the local
                                           // out-staging halves and PUSHED there by this worker's copy engine (the D2H machinery)
     bool peer_push = false;               // arguments live on worker 0 (another GPU): worker 0's copy engine PUSHES each wave's
@@ -484,7 +486,7 @@ static int numa_pinned_acquire(fbr_pool* p, uint64_t bytes, const std::vector<Nu
         const uint64_t lo = b.off / small * small, hi = std::min(mapped, round_up(b.off + b.len, small));
         bind_range_to_node((uint8_t*)ptr + lo, hi - lo, b.node);
     }
-    cudaError_t e = cudaHostRegister(ptr, mapped, cudaHostRegisterPortable);
+    cudaError_t e = cudaHostRegister(ptr, mapped, cudaHostRegisterPortable | cudaHostRegisterMapped);
     if (e != cudaSuccess) {
         munmap(ptr, mapped);
         return fail(FBR_ECUDA, "cudaHostRegister failed: %s", cudaGetErrorString(e));
@@ -887,7 +889,7 @@ static int finish_round(fbr_pool* p, SeqState& st, SeqPart& part, bool copy_wind
     CK(cudaStreamWaitEvent(w.s_out, w.ev_comp[last_rw], 0));
     CK(cudaStreamWaitEvent(w.s_out, w.ev_out[0], 0));      // copy-outs issued on either out stream are complete
     CK(cudaStreamWaitEvent(w.s_out, w.ev_out[1], 0));
-    if (copy_window && cx.full_window && !cx.out_dev && !cx.keep_on_device && part.count) {
+    if (copy_window && cx.full_window && !cx.out_dev && !cx.keep_on_device && !cx.zero_copy && part.count) {
         CK(cudaMemcpyAsync((uint8_t*)st.out + part.first * cx.R, cx.window_base, part.count * cx.R, cudaMemcpyDeviceToHost, w.s_out));
         STAT_ADD(p, d2h_bytes, part.count * cx.R);
     }
@@ -919,7 +921,15 @@ static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry
         static const bool out_off = getenv("FBR_PEER_OUT") && atoi(getenv("FBR_PEER_OUT")) == 0;
         cx.peer_out = cx.out_dev && part.worker != 0 && !cx.resilient && !out_off && !(d.flags & FBR_FULL_WINDOW);
     }
-    cx.full_window = (cx.out_dev && !cx.peer_out) || cx.resilient || cx.keep_on_device || (d.flags & FBR_FULL_WINDOW);
+    {
+        // Bit-packed bool results are small (1/8 B per task): instead of staging them in HBM and copying them out wave
+        // by wave (6 x (2 MB D2H + ~8 us set-up) = the critical path of the e2e step), the dispatch kernel can store them
+        // straight into the pinned host segment (zero copy): the PCIe writes spread over the whole kernel.
+        static const int zc = getenv("FBR_ZERO_COPY") ? atoi(getenv("FBR_ZERO_COPY")) : 0;
+        cx.zero_copy = zc != 0 && body.result_kind == FBR_RES_BITS8 && !cx.out_dev && !cx.resilient && !cx.keep_on_device &&
+                       !(d.flags & (FBR_FULL_WINDOW | FBR_SHUFFLE | FBR_VIA_RING | FBR_NO_ZERO_COPY)) && st.out != nullptr;
+    }
+    cx.full_window = (cx.out_dev && !cx.peer_out) || cx.resilient || cx.keep_on_device || (d.flags & FBR_FULL_WINDOW) || cx.zero_copy;
     cx.host_args = d.arg_stride != 0 && !cx.args_dev && !cx.resilient;
     {
         // device-resident arguments on worker 0, consumed by another worker: stream them through the staging halves,
@@ -1005,7 +1015,7 @@ static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry
         cx.direct = !env_off && !cx.resilient && !(d.flags & (FBR_SHUFFLE | FBR_VIA_RING)) && unit_ok && base_ok;
     }
     // wave capacity in claim units
-    uint64_t units_cap = cx.direct ? (1ull << 31) / std::max<uint32_t>(1, cx.slot_stride) :   // 32-bit unit counter
+    uint64_t units_cap = cx.direct ? (1ull << 31) :   // 32-bit unit counter; a direct wave needs no ring space
         std::min<uint64_t>(kRecCapacity, (cx.overlap ? p->ring_bytes / 2 : p->ring_bytes) / cx.slot_stride);
     if (cx.host_args) units_cap = std::min<uint64_t>(units_cap, p->ring_bytes / ((uint64_t)unit * d.arg_stride));
     if (!cx.full_window) units_cap = std::min<uint64_t>(units_cap, p->ring_bytes / ((uint64_t)unit * R));
@@ -1040,6 +1050,8 @@ static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry
     if (cx.full_window) {
         if (cx.out_dev) {
             cx.window_base = (uint8_t*)d.out + part.first * R;
+        } else if (cx.zero_copy) {
+            cx.window_base = (uint8_t*)st.out + part.first * R;     // pinned host memory, mapped into the device's address space (UVA)
         } else {
             CK(cudaMallocAsync(&part.d_window, std::max<uint64_t>(part.count * R, 16), w.s_in));
             cx.window_base = (uint8_t*)part.d_window;

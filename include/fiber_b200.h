@@ -153,6 +153,8 @@ int fbr_pool_worker_device(fbr_pool_t* pool, int worker, int* device_id);
 #define FBR_VIA_RING 0x1000u    /* always go through task records + result ring + gather_ordered, even for a
                                    contiguous block whose units could be stored at their final index by
                                    the dispatch kernel (direct placement) */
+#define FBR_NO_ZERO_COPY 0x2000u /* results are wanted wave by wave (imap): stage and copy them out instead of letting the kernel
+                                   store small results straight into the pinned segment */
 #define FBR_RESILIENT 0x400u    /* ResilientZPool semantics (fiber/pool.py:1425-1688): a claim unit whose
                                    worker dies (FBR_TASK_FAULT) is re-dispatched until it completes */
 
