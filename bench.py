@@ -844,6 +844,12 @@ def run_ours(args, dist):
     hbm_peak = float(peaks["hbm_gbs"])
     traffic, traffic_src = load_traffic()
     traffic_commit = traffic.get("_meta", {}).get("commit")
+    try:        # is the committed ncu capture from the very build being timed?
+        with open(os.path.join(ROOT, "fiber_b200", "_lib", "libfiber_b200.so"), "rb") as fh:
+            lib_sha = hashlib.sha256(fh.read()).hexdigest()
+    except OSError:
+        lib_sha = None
+    traffic_same_build = (lib_sha is not None and lib_sha == traffic.get("_meta", {}).get("lib_sha256"))
 
     def traffic_of(key):
         return traffic.get(key, {}).get("dram_bytes_per_launch")
@@ -909,6 +915,7 @@ def run_ours(args, dist):
                 "achieved": gather_bytes / (gather_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": gather_bytes / (gather_ms * 1e-3) / 1e9 / hbm_peak,
                 "traffic": traffic_of("gather_rows_kernel@prof_pi"), "traffic_source": traffic_src, "traffic_capture_commit": traffic_commit,
+                "traffic_capture_is_this_build": traffic_same_build,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": gather_bytes, "avg_launch_ms": gather_ms,
                 "step_ms_via_ring": 1e3 * t_ring / args.steps, "tasks_per_s_via_ring": world * PI_TASKS * args.steps / t_ring,

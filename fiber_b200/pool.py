@@ -622,7 +622,7 @@ class Pool:
     def _spec_of(func):
         return registry.spec(registry.body_name_of(func))
 
-    def map_async(self, func, iterable, chunksize=None, callback=None, error_callback=None):
+    def map_async(self, func, iterable, chunksize=None, callback=None, error_callback=None, _streaming=False):
         if error_callback:
             raise NotImplementedError
         self._check_running()
@@ -635,9 +635,12 @@ class Pool:
         if self._proc is not None:
             return self._submit_proc(spec, "map", iterable, chunksize)
         enc = spec.encode_map(iterable)
+        # imap wants ordered prefixes as they complete: results are staged and copied out wave by wave instead of being
+        # stored straight into the pinned segment by one kernel (zero copy, final only when the whole block is)
+        extra = _abi.FBR_NO_ZERO_COPY if _streaming else 0
         if self._results_bits and spec.name in registry.BITS_TWIN:
-            return self._submit_bits(func, spec, enc, _abi.FBR_MAP, chunksize)
-        return self._submit(func, enc, _abi.FBR_MAP, chunksize)
+            return self._submit_bits(func, spec, enc, _abi.FBR_MAP, chunksize, extra)
+        return self._submit(func, enc, _abi.FBR_MAP, chunksize, extra_flags=extra)
 
     def _submit_proc(self, spec, kind, items, chunksize, single=False):
         """Process-isolated workers: the map is cut into blocks that worker processes pull (procpool.py)."""
@@ -650,12 +653,12 @@ class Pool:
         self.sent_tasks += len(items)
         return r
 
-    def _submit_bits(self, func, spec, enc, kind, chunksize):
+    def _submit_bits(self, func, spec, enc, kind, chunksize, extra_flags=0):
         """A bool needs one bit: the twin body evaluates 8 consecutive items (range() indices or argument
         records) per result byte, so the ring, the ordered output and the D2H copy move n/8 bytes."""
         twin = registry.spec(registry.BITS_TWIN[spec.name])
         n_items = enc.n
-        r = self._submit(func, twin.from_encoded(enc), kind, max(1, chunksize // 8), spec=twin)
+        r = self._submit(func, twin.from_encoded(enc), kind, max(1, chunksize // 8), spec=twin, extra_flags=extra_flags)
         r._n_items, r._user_spec = n_items, spec
         self.sent_tasks += n_items - r._n
         return r
@@ -703,11 +706,11 @@ class Pool:
         return self.apply_async(func, args, kwds).get()
 
     def imap(self, func, iterable, chunksize=1):
-        r = self.map_async(func, iterable, chunksize)
+        r = self.map_async(func, iterable, chunksize, _streaming=True)
         return iter(r.get()) if self._proc is not None else r.iget_ordered()
 
     def imap_unordered(self, func, iterable, chunksize=1):
-        r = self.map_async(func, iterable, chunksize)
+        r = self.map_async(func, iterable, chunksize, _streaming=True)
         return iter(r.get()) if self._proc is not None else r.iget_unordered()
 
     # -- shutdown (fiber/pool.py:1332-1403) -----------------------------------------------------------

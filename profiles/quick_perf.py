@@ -15,8 +15,10 @@ def report(tag, st):
     g_ms = st["gather_ms"] / max(1, st["gather_launches"])
     d_b = st["dispatch_bytes"] / max(1, st["dispatch_launches"])
     g_b = st["gather_bytes"] / max(1, st["gather_launches"])
-    print("%-10s dispatch %.4f ms (%.0f GB/s, %.1f%%)   gather %.4f ms (%.0f GB/s, %.1f%%)" % (
-        tag, d_ms, d_b / d_ms / 1e6, 100 * d_b / d_ms / 1e6 / PEAK, g_ms, g_b / g_ms / 1e6, 100 * g_b / g_ms / 1e6 / PEAK), flush=True)
+    line = "%-10s dispatch %.4f ms (%.0f GB/s, %.1f%%)" % (tag, d_ms, d_b / d_ms / 1e6, 100 * d_b / d_ms / 1e6 / PEAK)
+    if st["gather_launches"]:      # direct-placement maps launch no gather
+        line += "   gather %.4f ms (%.0f GB/s, %.1f%%)" % (g_ms, g_b / g_ms / 1e6, 100 * g_b / g_ms / 1e6 / PEAK)
+    print(line, flush=True)
 
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
