@@ -321,14 +321,15 @@ __global__ void __launch_bounds__(kThreads) dispatch_pi_bits_kernel(const WavePa
 }
 
 // ================================================================================================
-// dispatch: bit-packed twin of a bool ThreadBody with EXPLICIT argument items (B::Arg records, 8 per
-// byte-task).  A warp takes 512 consecutive items per pass: lane l evaluates items l, l+32, ... (each
-// load instruction reads 32 consecutive records: fully coalesced), and the ballot of pass j IS word j
+// dispatch: bit-packed twin of ANY bool ThreadBody: 8 items per byte-task, items being explicit argument
+// records (B::Arg, kIndex = false) or range() indices (kIndex = true: item i is index_start + i*index_step,
+// no argument bytes).  A warp takes 512 consecutive items per pass: lane l evaluates items l, l+32, ...
+// (each load instruction reads 32 consecutive records: fully coalesced), and the ballot of pass j IS word j
 // of the warp's 64 output bytes (bit l = lane l's result = item 32j + l) -- no shuffles, no transposes.
 // Lanes 0..15 store the 16 words: 64 contiguous bytes per warp.  Items at or past wp.n_items are not
-// read and leave zero bits.  Algorithmic bytes per item: sizeof(Arg) read + 1/8 written.
+// evaluated and leave zero bits.  Algorithmic bytes per item: sizeof(Arg) read + 1/8 written.
 // ================================================================================================
-template <class B>
+template <class B, bool kIndex = false>
 __global__ void __launch_bounds__(kThreads) dispatch_bits_items_kernel(const WaveParams wp) {
     using Arg = typename B::Arg;
     static_assert(!B::kCanFault, "bit-packed twins are for bodies that cannot lose a unit");
@@ -354,7 +355,9 @@ __global__ void __launch_bounds__(kThreads) dispatch_bits_items_kernel(const Wav
                 const uint32_t i = base + 32u * j + lane;
                 bool r = false;
                 if (i < n_it && item0 + i < wp.n_items) {
-                    const Arg a = *reinterpret_cast<const Arg*>(uargs + (size_t)i * sizeof(Arg));
+                    Arg a;
+                    if constexpr (kIndex) a = (Arg)(wp.index_start + (int64_t)(item0 + i) * wp.index_step);
+                    else a = *reinterpret_cast<const Arg*>(uargs + (size_t)i * sizeof(Arg));
                     r = B::run(a, wp.index_base + item0 + i, es, rec.attempt) != 0;
                 }
                 const uint32_t word = __ballot_sync(0xffffffffu, r);

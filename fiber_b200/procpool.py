@@ -100,7 +100,7 @@ def gpu_worker_main(device, conn, results, sys_path):
         _, job, blk, body, kind, chunksize, payload, shm_name, off, attempt, module = msg
         try:
             if module is not None and body not in registry.body_names():
-                registry.register_module(body, module[0], module[1], module[2])
+                registry.register_module(body, *module)
             f = proxies.get(body) or proxies.setdefault(body, _proxy_for(body))
             items = range(*payload[1]) if payload[0] == "range" else pickle.loads(payload[1])
             pool._attempt = attempt

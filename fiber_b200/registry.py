@@ -21,7 +21,7 @@ from . import _abi
 _BOUND = {}  # callables that cannot carry attributes (builtins) -> body name
 
 
-def device_body(name, source=None, entry="fbr_body_entry", args="i64", **meta):
+def device_body(name, source=None, entry="fbr_body_entry", args="i64", bits_entry=None, **meta):
     """Decorator: ``@device_body("pi_inside_det")`` binds ``func`` to the device body ``name`` and sets
     ``func.__fiber_meta__`` (``gpu=1`` unless overridden), like ``fiber.meta``.
 
@@ -31,7 +31,9 @@ def device_body(name, source=None, entry="fbr_body_entry", args="i64", **meta):
     nvcc (cached by content hash under ``fiber_b200/_lib/bodies/``) and registered with
     ``fbr_register_body`` -- the reference ships any callable to its workers (fiber/pool.py:961); this is
     how a callable that is not compiled into libfiber_b200 gets its device code there.  ``args`` names the
-    argument record layout: ``"i64"`` (one int) or ``"i64x2"`` (two ints)."""
+    argument record layout: ``"i64"`` (one int) or ``"i64x2"`` (two ints).  A bool body may also export its
+    bit-packed twin (``FBR_EXPORT_BOOL_BODY_BITS(Body, "<name>_bits8", <bits_entry>, flags)``): pass ``bits_entry``
+    and its results travel one bit each, like the compiled-in bool body's."""
     from .meta import VALID_META_KEYS
     for k in meta:
         assert k in VALID_META_KEYS, "Invalid meta argument \"{}\"".format(k)
@@ -39,7 +41,7 @@ def device_body(name, source=None, entry="fbr_body_entry", args="i64", **meta):
     md.update(meta)
     if source is not None:
         from . import bodies
-        register_module(name, bodies.compile_module(name, source), entry, args)
+        register_module(name, bodies.compile_module(name, source), entry, args, bits_entry)
 
     def decorator(func):
         bind(func, name, **md)
@@ -55,10 +57,16 @@ def module_of(name):
     return _MODULES.get(name)
 
 
-def register_module(name, module_path, entry="fbr_body_entry", args="i64"):
-    """``fbr_register_body`` + the host-side encoder for the body's argument records."""
+def register_module(name, module_path, entry="fbr_body_entry", args="i64", bits_entry=None):
+    """``fbr_register_body`` + the host-side encoder for the body's argument records (and, with ``bits_entry``, the
+    body's bit-packed twin ``<name>_bits8``)."""
     import ctypes
-    _MODULES[name] = (str(module_path), entry, args)
+    _MODULES[name] = (str(module_path), entry, args, bits_entry)
+    if bits_entry is not None:
+        twin = name + "_bits8"
+        register_module(twin, module_path, bits_entry, "bits8")
+        _MODULES.pop(twin, None)
+        BITS_TWIN[name] = twin
     L = _abi.load()
     fid = ctypes.c_int(-1)
     _abi.check(L.fbr_register_body(name.encode(), str(module_path).encode(), entry.encode(), ctypes.byref(fid)))
@@ -70,8 +78,10 @@ def register_module(name, module_path, entry="fbr_body_entry", args="i64"):
             specs[name] = _UnaryI64(info)
         elif args == "i64x2":
             specs[name] = _BinaryI64(info)
+        elif args == "bits8":
+            specs[name] = _Bits8(info)
         else:
-            raise ValueError("unknown argument layout %r (have: i64, i64x2)" % (args,))
+            raise ValueError("unknown argument layout %r (have: i64, i64x2, bits8)" % (args,))
     return specs[name]
 
 

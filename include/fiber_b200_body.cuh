@@ -56,6 +56,43 @@ int occupancy(int index_mode) {
 }
 }  // namespace fbr_body_export
 
+namespace fbr_body_export {
+// the bit-packed twin of a bool body: 8 items (explicit records or range() indices) per result byte
+template <class B>
+void launch_bits(const void* wpv, int grid, void* sv) {
+    const fbr::WaveParams& wp = *(const fbr::WaveParams*)wpv;
+    cudaStream_t s = (cudaStream_t)sv;
+    if constexpr (B::kIndexArg) {
+        if (wp.arg_stride == 0) {
+            fbr::dispatch_bits_items_kernel<B, true><<<grid, fbr::kThreads, 0, s>>>(wp);
+            return;
+        }
+    }
+    fbr::dispatch_bits_items_kernel<B, false><<<grid, fbr::kThreads, 0, s>>>(wp);
+}
+template <class B>
+int occupancy_bits(int index_mode) {
+    int occ = 0;
+    const void* k = (const void*)fbr::dispatch_bits_items_kernel<B, false>;
+    if constexpr (B::kIndexArg) {
+        if (index_mode) k = (const void*)fbr::dispatch_bits_items_kernel<B, true>;
+    }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, fbr::kThreads, 0) != cudaSuccess) { cudaGetLastError(); return 1; }
+    return occ > 0 ? occ : 1;
+}
+}  // namespace fbr_body_export
+
+// A bool body (Res = uint8_t, 0/1) additionally exports its bit-packed twin "<name>_bits8" (result kind
+// FBR_RES_BITS8, 8 items per task): register both and bool results travel one bit each.
+#define FBR_EXPORT_BOOL_BODY_BITS(Body, twin_name, entry, body_flags)                                              \
+    extern "C" const fbr_body_module_t* entry(void) {                                                            \
+        static const fbr_body_module_t m = {FBR_BODY_MODULE_ABI, (uint32_t)sizeof(fbr::WaveParams), twin_name,   \
+                                            8u * (uint32_t)sizeof(typename Body::Arg), 1u, (uint32_t)FBR_RES_BITS8, \
+                                            (uint32_t)(body_flags), 512u,                                        \
+                                            fbr_body_export::launch_bits<Body>, fbr_body_export::occupancy_bits<Body>}; \
+        return &m;                                                                                               \
+    }
+
 // Body: a ThreadBody (see bodies.cuh) whose Res is 1 or 8 bytes.  result_kind: FBR_RES_BOOL / FBR_RES_I64 / ...
 #define FBR_EXPORT_THREAD_BODY(Body, body_name, entry, kind, body_flags)                                         \
     extern "C" const fbr_body_module_t* entry(void) {                                                            \

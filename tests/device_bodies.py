@@ -43,6 +43,8 @@ struct OddBits {
     }
 };
 FBR_EXPORT_THREAD_BODY(OddBits, "odd_bits", odd_bits_entry, FBR_RES_BOOL, FBR_BODY_INDEX_ARG | FBR_BODY_SUMMABLE)
+// ... and its bit-packed twin: 8 items (range() indices or int64 records) per result byte
+FBR_EXPORT_BOOL_BODY_BITS(OddBits, "odd_bits_bits8", odd_bits_bits_entry, FBR_BODY_INDEX_ARG | FBR_BODY_SUMMABLE)
 '''
 
 
@@ -57,7 +59,7 @@ def collatz_steps(x):
     return steps
 
 
-@fiber_b200.device_body("odd_bits", source=ODD_BITS_SRC, entry="odd_bits_entry")
+@fiber_b200.device_body("odd_bits", source=ODD_BITS_SRC, entry="odd_bits_entry", bits_entry="odd_bits_bits_entry")
 def odd_bits(x):
     return bin(x & (2 ** 64 - 1)).count("1") % 2 == 1
 

@@ -290,13 +290,16 @@ def test_out_of_tree_body_registration():
     from . import device_bodies as D
     lib = _abi.load()
     n = ctypes.c_int(0)
-    assert lib.fbr_body_count(ctypes.byref(n)) == 0 and n.value >= 15
+    assert lib.fbr_body_count(ctypes.byref(n)) == 0 and n.value >= 16
     s = registry.spec("collatz_steps")
     assert s.func_id >= 13 and (s.arg_bytes, s.result_bytes, s.result_kind) == (8, 8, _abi.FBR_RES_I64)
     assert s.flags & _abi.FBR_BODY_INDEX_ARG and registry.body_name_of(D.collatz_steps) == "collatz_steps"
     assert s.encode_map(range(1, 10)).arg_stride == 0 and s.encode_map([3, 4]).args.tolist() == [3, 4]
     b = registry.spec("odd_bits")
     assert (b.arg_bytes, b.result_bytes, b.result_kind) == (8, 1, _abi.FBR_RES_BOOL)
+    t = registry.spec("odd_bits_bits8")                   # the module's bit-packed twin, registered with it
+    assert (t.arg_bytes, t.result_bytes, t.result_kind) == (64, 1, _abi.FBR_RES_BITS8) and registry.BITS_TWIN["odd_bits"] == "odd_bits_bits8"
+    assert registry.module_of("odd_bits")[3] == "odd_bits_bits_entry"
     fid = ctypes.c_int(-1)
     assert lib.fbr_body_lookup(b"odd_bits", ctypes.byref(fid)) == 0 and fid.value == b.func_id
     assert lib.fbr_register_body(b"x", b"/nonexistent.so", b"e", ctypes.byref(fid)) == _abi.FBR_ENOENT

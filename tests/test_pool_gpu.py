@@ -711,10 +711,21 @@ def test_out_of_tree_bodies_bit_exact():
     assert pool.apply(D.collatz_steps, (27,)) == 111
     with pytest.raises(ValueError, match="bad argument in task 3"):
         pool.map(D.collatz_steps, [5, 6, 7, 0, 9])
-    # a registered bool body: one byte per result, placed by the same dispatch kernel template
-    ob = pool.map(D.odd_bits, range(-5000, 200000))
-    assert np.array_equal(np.asarray(ob), D.odd_bits_np(np.arange(-5000, 200000))) and ob.sum() == int(D.odd_bits_np(np.arange(-5000, 200000)).sum())
+    # a registered bool body: its module also exports the bit-packed twin, so its results travel one bit each -- over a
+    # range() and over explicit argument records -- and one byte each on a results="bytes" pool
+    want_ob = D.odd_bits_np(np.arange(-5000, 200003))
+    ob = pool.map(D.odd_bits, range(-5000, 200003))
+    assert ob.packed is not None and ob.packed.nbytes == (205003 + 7) // 8
+    assert np.array_equal(np.asarray(ob), want_ob) and ob.sum() == int(want_ob.sum())
     assert ob[:100] == [D.odd_bits(x) for x in range(-5000, -4900)]
+    xs_ob = np.random.default_rng(4).integers(-2 ** 62, 2 ** 62, size=70001, dtype=np.int64)
+    ob2 = pool.map(D.odd_bits, xs_ob)
+    assert ob2.packed is not None and np.array_equal(np.asarray(ob2), D.odd_bits_np(xs_ob)) and ob2.sum() == int(D.odd_bits_np(xs_ob).sum())
+    bp = fiber_b200.Pool(1, results="bytes")
+    ob3 = bp.map(D.odd_bits, range(-5000, 200003))
+    assert ob3.packed is None and np.array_equal(np.asarray(ob3), want_ob)
+    bp.terminate()
+    bp.join()
     # placement by index under shuffled arrival + resilient pool work for registered bodies too
     pool.terminate()
     pool.join()
