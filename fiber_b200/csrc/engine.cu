@@ -897,20 +897,30 @@ static int finish_round(fbr_pool* p, SeqState& st, SeqPart& part, bool copy_wind
     const PartCtx& cx = part.cx;
     const int slot = part.ctrl_slot;
     const int last_rw = (int)((w.wave_no - 1) % kRecWindows);
-    CK(cudaStreamWaitEvent(w.s_out, w.ev_comp[last_rw], 0));
-    CK(cudaStreamWaitEvent(w.s_out, w.ev_out[0], 0));      // copy-outs issued on either out stream are complete
-    CK(cudaStreamWaitEvent(w.s_out, w.ev_out[1], 0));
+    // A block whose results never pass through the copy-out stream (device-resident output, zero-copy stores into the
+    // pinned segment) finishes on the compute stream itself: its control block follows its last kernel without a
+    // cross-stream hop.  Everything else finishes on s_out, behind its copy-outs.
+    // (Off: a copy on the compute stream puts a DMA hop between back-to-back kernels of pipelined maps, which costs
+    // them what a blocking map() gains.  FBR_FINISH_ON_COMP=1 enables it for A/B runs.)
+    static const bool finish_on_comp = getenv("FBR_FINISH_ON_COMP") && atoi(getenv("FBR_FINISH_ON_COMP")) != 0;
+    const bool on_comp = finish_on_comp && cx.direct && cx.full_window && !cx.resilient && (cx.zero_copy || cx.out_dev || cx.keep_on_device);
+    cudaStream_t sf = on_comp ? w.s_comp : w.s_out;
+    if (!on_comp) {
+        CK(cudaStreamWaitEvent(w.s_out, w.ev_comp[last_rw], 0));
+        CK(cudaStreamWaitEvent(w.s_out, w.ev_out[0], 0));      // copy-outs issued on either out stream are complete
+        CK(cudaStreamWaitEvent(w.s_out, w.ev_out[1], 0));
+    }
     if (copy_window && cx.full_window && !cx.out_dev && !cx.keep_on_device && !cx.zero_copy && part.count) {
-        CK(cudaMemcpyAsync((uint8_t*)st.out + part.first * cx.R, cx.window_base, part.count * cx.R, cudaMemcpyDeviceToHost, w.s_out));
+        CK(cudaMemcpyAsync((uint8_t*)st.out + part.first * cx.R, cx.window_base, part.count * cx.R, cudaMemcpyDeviceToHost, sf));
         STAT_ADD(p, d2h_bytes, part.count * cx.R);
     }
-    CK(cudaMemcpyAsync(&w.h_ctrl[slot], &w.d_ctrl[slot], sizeof(SeqCtrl), cudaMemcpyDeviceToHost, w.s_out));
+    CK(cudaMemcpyAsync(&w.h_ctrl[slot], &w.d_ctrl[slot], sizeof(SeqCtrl), cudaMemcpyDeviceToHost, sf));
     if (cx.resilient && part.lost_cap)
-        CK(cudaMemcpyAsync(part.h_lost, part.d_lost, sizeof(LostUnit) * part.lost_cap, cudaMemcpyDeviceToHost, w.s_out));
+        CK(cudaMemcpyAsync(part.h_lost, part.d_lost, sizeof(LostUnit) * part.lost_cap, cudaMemcpyDeviceToHost, sf));
     // one event per part for its whole life, re-recorded every round: another waiter may hold the handle
     // (fbr_result_wait blocks on it outside the pool lock), so it must never be destroyed under it
     if (!part.done) CK(cudaEventCreateWithFlags(&part.done, cudaEventDisableTiming));
-    CK(cudaEventRecord(part.done, w.s_out));
+    CK(cudaEventRecord(part.done, sf));
     return FBR_OK;
 }
 
@@ -1064,6 +1074,7 @@ static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry
             cx.window_base = (uint8_t*)d.out + part.first * R;
         } else if (cx.zero_copy) {
             cx.window_base = (uint8_t*)st.out + part.first * R;     // pinned host memory, mapped into the device's address space (UVA)
+            STAT_ADD(p, d2h_bytes, part.count * (uint64_t)R);        // these bytes cross PCIe as the kernel's own stores
         } else {
             CK(cudaMallocAsync(&part.d_window, std::max<uint64_t>(part.count * R, 16), w.s_in));
             cx.window_base = (uint8_t*)part.d_window;
