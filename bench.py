@@ -80,6 +80,18 @@ def load_imad_peak():
         return {"gops": None, "source": "unavailable", "pi_body_screened_tasks_per_s": "n/a"}
 
 
+def source_digest():
+    """sha256 over the CUDA sources and headers of the library, in sorted order (same recipe as profiles/run_ncu.sh)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "fiber_b200", "csrc", "*.cu")) + glob.glob(os.path.join(ROOT, "fiber_b200", "csrc", "*.cuh")) +
+                   glob.glob(os.path.join(ROOT, "include", "*.h")) + glob.glob(os.path.join(ROOT, "include", "*.cuh")))
+    h = hashlib.sha256()
+    for f in files:
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def load_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch (and the capture's commit) from the committed
     `ncu --set full` capture of profiles/prof_target.py (same kernels, same sizes); newest round wins."""
@@ -844,12 +856,9 @@ def run_ours(args, dist):
     hbm_peak = float(peaks["hbm_gbs"])
     traffic, traffic_src = load_traffic()
     traffic_commit = traffic.get("_meta", {}).get("commit")
-    try:        # is the committed ncu capture from the very build being timed?
-        with open(os.path.join(ROOT, "fiber_b200", "_lib", "libfiber_b200.so"), "rb") as fh:
-            lib_sha = hashlib.sha256(fh.read()).hexdigest()
-    except OSError:
-        lib_sha = None
-    traffic_same_build = (lib_sha is not None and lib_sha == traffic.get("_meta", {}).get("lib_sha256"))
+    # is the committed ncu capture from the very sources being timed?  (nvcc output is not bit-reproducible, so the
+    # build is identified by the digest of its sources, written by profiles/run_ncu.sh next to the captures)
+    traffic_same_build = source_digest() == traffic.get("_meta", {}).get("src_sha256")
 
     def traffic_of(key):
         return traffic.get(key, {}).get("dram_bytes_per_launch")

@@ -99,12 +99,12 @@ def main():
         return sum(v) / len(v) if v else None
     summary = {k: {"dram_bytes_per_launch": mean(t["dram"]), "lts_pct_of_peak": mean(t["lts_pct"]), "lts_bytes_per_launch": mean(t["lts_bytes"]),
                    "ncu_time_us": mean(t["us"]), "launches": len(t["dram"])} for k, t in traffic.items()}
-    lib_sha = None
+    src_sha = None
     try:
-        lib_sha = open(os.path.join(OUT, "lib_sha256.txt")).read().strip()
+        src_sha = open(os.path.join(OUT, "src_sha256.txt")).read().strip()
     except OSError:
         pass
-    summary["_meta"] = {"commit": git_head(), "lib_sha256": lib_sha,
+    summary["_meta"] = {"commit": git_head(), "src_sha256": src_sha,
                         "how": "ncu --set full --clock-control none (profiles/run_ncu.sh); caches are flushed between replays, times are cold"}
     with open(os.path.join(ROOT, "profiles", tag + "_traffic.json"), "w") as fh:
         json.dump(summary, fh, indent=1, sort_keys=True)
