@@ -353,8 +353,17 @@ class ProcessPool:
                     except (EOFError, OSError):
                         msg, dead_reason = None, "connection lost (exit code %s)" % w.proc.exitcode
                     if msg is not None:
+                        # a block of an EARLIER map (one that failed while this block was still running) reports late:
+                        # the worker becomes idle again, the current map's accounting is not touched
+                        mine = w.block is not None and w.block[0] is job and msg[0] != "ready" and msg[1] == job.id
                         if msg[0] == "ready":
                             w.ready = True
+                        elif not mine:
+                            if msg[0] == "dead":
+                                w.block = None
+                                dead_reason = msg[3]
+                            else:
+                                w.block = None
                         elif msg[0] == "done":
                             job.sum += msg[3] or 0
                             job.done_blocks += 1
@@ -370,7 +379,7 @@ class ProcessPool:
                 elif w.proc is not None and w.proc.sentinel in ready and not w.proc.is_alive():
                     dead_reason = "process exited with code %s" % w.proc.exitcode
                 if dead_reason is not None:
-                    if w.block is not None:
+                    if w.block is not None and w.block[0] is job:
                         inflight -= 1
                     self._on_death(w, dead_reason)
         job.event.set()

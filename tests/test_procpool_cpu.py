@@ -44,6 +44,16 @@ def test_blocks_are_pulled_and_placed_by_index():
         with pytest.raises(OverflowError):
             pool.submit(_Spec("square_i64"), None, "map", [1, 2, 3037000500], 32).get(60)
         assert pool.submit(_Spec("square_i64"), None, "map", [3], 32).get(60) == [9]        # the pool keeps serving
+        # a map that fails in its first block while its other blocks are still running: their late reports must not
+        # leak into the next map's accounting
+        bad = np.concatenate([[3037000500], np.arange(4 * BLOCK_ALIGN)]).astype(np.int64)
+        h_bad = pool.submit(_Spec("square_i64"), None, "map", bad, 32)
+        h_next = pool.submit(_Spec("identity_i64"), None, "map", range(3 * BLOCK_ALIGN + 5), 32)
+        with pytest.raises(OverflowError):
+            h_bad.get(60)
+        r = h_next.get(60)
+        m = 3 * BLOCK_ALIGN + 5
+        assert np.array_equal(np.asarray(r), np.arange(m)) and r.sum() == m * (m - 1) // 2
     finally:
         pool.terminate()
         pool.join()
