@@ -17,6 +17,7 @@ replaced by a fresh process.  Everything a worker computes still runs through th
 fallback here either.
 """
 import collections
+import mmap
 import multiprocessing as mp
 import multiprocessing.connection as mpc
 import os
@@ -24,7 +25,6 @@ import pickle
 import sys
 import threading
 import time
-import mmap
 import weakref
 
 import numpy as np

@@ -4,7 +4,6 @@ worker that dies has its block re-queued with attempt + 1 and is replaced (fiber
 import numpy as np
 import pytest
 
-from fiber_b200 import registry
 from fiber_b200.procpool import BLOCK_ALIGN, ProcessPool, WorkerDied
 
 from ._fake_worker import fake_worker_main
