@@ -344,6 +344,8 @@ struct SeqState {
     fbr_map_desc_t desc;
     std::vector<SeqPart> parts;
     std::vector<SeqPart> graveyard;        // parts that were running on a worker when it died (their blocks were re-dispatched)
+    int waiters = 0;                       // threads inside fbr_result_wait for this seq (they hold event handles outside the lock)
+    bool release_pending = false;          // fbr_result_release arrived while they were waiting: the last one out frees the seq
     int dead_worker = -1;                  // a worker died under this map and the map could not be re-dispatched
     int dead_error = 0;
 };
@@ -1775,8 +1777,34 @@ static int dead_map_error(fbr_pool* p, const SeqState& st) {
                                            : "the pool was created without error_handling, so its blocks are not re-dispatched");
 }
 
+static int result_wait_locked_out(fbr_pool_t* p, uint64_t seq, int timeout_ms, fbr_result_t* res);
+
+// A waiter blocks on CUDA events OUTSIDE the pool lock; a concurrent fbr_result_release must not destroy them under it.
+// Waiters are counted per seq; a release that arrives meanwhile is deferred to the last waiter leaving.
 int fbr_result_wait(fbr_pool_t* p, uint64_t seq, int timeout_ms, fbr_result_t* res) {
     if (!p || !res) return fail(FBR_EINVAL, "NULL argument");
+    {
+        std::lock_guard<std::mutex> g(p->mu);
+        auto it = p->seqs.find(seq);
+        if (it == p->seqs.end()) return fail(FBR_ENOENT, "unknown seq %llu", (unsigned long long)seq);
+        it->second->waiters++;
+    }
+    const int rc = result_wait_locked_out(p, seq, timeout_ms, res);
+    const std::string msg = rc != FBR_OK ? g_err : std::string();
+    {
+        std::lock_guard<std::mutex> g(p->mu);
+        auto it = p->seqs.find(seq);
+        if (it != p->seqs.end() && --it->second->waiters == 0 && it->second->release_pending) {
+            harvest(p, *it->second);
+            free_seq(p, *it->second);
+            p->seqs.erase(it);
+        }
+    }
+    if (rc != FBR_OK) g_err = msg;
+    return rc;
+}
+
+static int result_wait_locked_out(fbr_pool_t* p, uint64_t seq, int timeout_ms, fbr_result_t* res) {
     const auto deadline = std::chrono::steady_clock::now() + std::chrono::milliseconds(timeout_ms < 0 ? 0 : timeout_ms);
     for (;;) {
         struct Ev { int worker, device; cudaEvent_t ev; };
@@ -1960,6 +1988,10 @@ int fbr_result_release(fbr_pool_t* p, uint64_t seq) {
     std::lock_guard<std::mutex> g(p->mu);
     auto it = p->seqs.find(seq);
     if (it == p->seqs.end()) return fail(FBR_ENOENT, "unknown seq %llu", (unsigned long long)seq);
+    if (it->second->waiters > 0) {        // another thread is blocked on this map's events: it frees the seq when it leaves
+        it->second->release_pending = true;
+        return FBR_OK;
+    }
     harvest(p, *it->second);  // keeps the timing statistics of maps released without a wait
     free_seq(p, *it->second);
     p->seqs.erase(it);
