@@ -7,7 +7,8 @@ n_gpus = int(sys.argv[1]); n_total = int(sys.argv[2]) if len(sys.argv) > 2 else 
 lib = _abi.load()
 ids = (ctypes.c_int * n_gpus)(*range(n_gpus))
 h = ctypes.c_void_p()
-_abi.check(lib.fbr_pool_create(n_gpus, ids, (n_total // n_gpus + 4096) * 4096, _abi.FBR_POOL_TIMING, ctypes.byref(h)))
+ring = int(os.environ.get("PEER_RING_MB", "256")) << 20      # staging halves: the largest wave of the NVLink pipeline
+_abi.check(lib.fbr_pool_create(n_gpus, ids, ring, _abi.FBR_POOL_TIMING, ctypes.byref(h)))
 din, dout = ctypes.c_void_p(), ctypes.c_void_p()
 _abi.check(lib.fbr_device_alloc(h, 0, n_total * 4096, ctypes.byref(din)))
 _abi.check(lib.fbr_device_alloc(h, 0, n_total * 4096, ctypes.byref(dout)))
