@@ -543,7 +543,7 @@ def fused_peer_map(n_gpus, n_total, steps):
     lib = _abi.load()
     ids = (ctypes.c_int * n_gpus)(*range(n_gpus))
     h = ctypes.c_void_p()
-    _abi.check(lib.fbr_pool_create(n_gpus, ids, 256 << 20, 0, ctypes.byref(h)))     # staging halves of 256 MiB: the largest wave
+    _abi.check(lib.fbr_pool_create(n_gpus, ids, 64 << 20, 0, ctypes.byref(h)))      # staging halves of 64 MiB = one wave
     try:
         din, dout = ctypes.c_void_p(), ctypes.c_void_p()
         _abi.check(lib.fbr_device_alloc(h, 0, n_total * 4096, ctypes.byref(din)))
@@ -587,7 +587,7 @@ def fused_peer_map(n_gpus, n_total, steps):
                "direct_waves": int(st.direct_waves), "gather_launches": int(st.gather_launches),
                "note": "in-process Pool(%d): args/out on GPU 0; each wave of a non-root worker's block is pushed into its staging by "
                        "the root's copy engine, mapped locally, and pushed back into the root's output by the worker's copy engine "
-                       "(posted writes both ways, pyramid wave schedule); FBR_PEER_PUSH=0 FBR_PEER_OUT=0 selects the single-kernel "
+                       "(posted writes both ways, 64 MB waves); FBR_PEER_PUSH=0 FBR_PEER_OUT=0 selects the single-kernel "
                        "variant with peer loads + stores" % n_gpus}
         if c0 and c1:
             out["nvml_gpu0_nvlink"] = {"tx_GBps": (c1[0] - c0[0]) / dt / 1e9, "rx_GBps": (c1[1] - c0[1]) / dt / 1e9,

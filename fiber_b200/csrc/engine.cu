@@ -1061,7 +1061,8 @@ static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry
         if (body.result_kind == FBR_RES_BITS8 && !cx.host_args) n_waves = 6;
         if (const char* e = getenv("FBR_WAVES")) n_waves = std::max<uint64_t>(1, (uint64_t)atoll(e));                          // tuning knob
         const uint64_t share = round_up((part.count + n_waves - 1) / n_waves, unit);
-        if (!(cx.peer_push || cx.peer_out))      // NVLink-staged blocks use the whole staging half (pyramid schedule below)
+        static const bool pyr = getenv("FBR_PYRAMID") && atoi(getenv("FBR_PYRAMID")) != 0;
+        if (!(pyr && (cx.peer_push || cx.peer_out)))      // (the pyramid schedule uses the whole staging half)
             cx.wave_tasks_cap = std::min(cx.wave_tasks_cap, std::max(min_wave_tasks, share));
     }
 
@@ -1106,11 +1107,12 @@ static int submit_part(fbr_pool* p, SeqState& st, SeqPart& part, const BodyEntry
     const bool taper = taper_on && streaming_out;
     const bool ramp = ramp_on && streaming_out && part.count > 4 * cx.wave_tasks_cap;
     const uint64_t min_tail_tasks = round_up(std::max<uint64_t>(1, (256ull << 10) / std::max<uint32_t>(1, R)), unit);
-    // Blocks streamed over NVLink by copy engines (root-resident maps): a peer copy costs ~20 us of set-up whatever its
-    // size (two-way 764 GB/s in one piece, 613 GB/s in 64 MB pieces: profiles/r02_peer_copy.txt), and the pipeline pays
-    // one wave's copy at each end.  So the waves form a pyramid: they double from cap/16 up to the staging capacity and
-    // halve again towards the end -- few, large copies in the middle, short fill and drain.  (FBR_PYRAMID=0: equal waves.)
-    static const bool pyramid_on = !(getenv("FBR_PYRAMID") && atoi(getenv("FBR_PYRAMID")) == 0);
+    // Blocks streamed over NVLink by copy engines (root-resident maps).  Raw peer copies reach 764 GB/s each way in one
+    // piece and 613 GB/s in 64 MB pieces (profiles/r02_peer_copy.txt), which suggested a pyramid of waves -- doubling
+    // from cap/16 up to the staging capacity, halving again towards the end: few large copies, short fill and drain.
+    // Measured on 2 GPUs (profiles/r02_peer_sweep.txt): 3.47 ms against 3.38 (equal 256 MB waves) and 3.27-3.41 (equal
+    // 64 MB waves) -- no gain, so equal waves stay the default (FBR_PYRAMID=1 enables the pyramid).
+    static const bool pyramid_on = getenv("FBR_PYRAMID") && atoi(getenv("FBR_PYRAMID")) != 0;
     const bool pyramid = pyramid_on && (cx.peer_push || cx.peer_out);
     const uint64_t pyr_base = round_up(std::max<uint64_t>(unit, cx.wave_tasks_cap / 16), unit);
     uint64_t done_tasks = 0;
