@@ -812,7 +812,7 @@ def run_parzen(dev, traffic, with_cpu):
                zip(f64.tolist(), widths, [int(round(d * h * n)) for h, d in f64.tolist()]))
     kern_us = out["starmap_chunksize1"]["kernel_us_per_job"]
     l2_bytes = len(widths) * n * xs.shape[1] * 4
-    tr = traffic.get("dispatch_parzen_kernel@prof_parzen", {})
+    tr = traffic.get("dispatch_parzen_kernel<float>@prof_parzen", {})
     out.update({
         "value": out["starmap_chunksize1"]["tasks_per_s"], "unit": "tasks/s",
         "parity": {"k_n_equals_fp32_oracle_and_within_boundary_of_fp64": bool(ok), "fp32_vs_fp64_k_n_mismatches": mism,
