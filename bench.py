@@ -501,7 +501,12 @@ def run_reference(args, dist):
     if dist.rank != 0:
         return
     cores = os.cpu_count() or 1
-    res, kind = cpu_arm("pi", cores, reps=max(1, args.steps), warm=max(0, min(args.warmup, 1)))
+    try:
+        res, kind = cpu_arm("pi", cores, reps=max(1, args.steps), warm=max(0, min(args.warmup, 1)),
+                            timeout=max(420, 30 + 6 * max(1, args.steps)))
+    except Exception as e:      # noqa: BLE001 -- neither the reference copy nor its port could run: say so, exit 0
+        print(json.dumps({"impl": "reference", "unavailable": str(e)[:300]}), flush=True)
+        return
     times = res["times"]
     total = sum(times)
     value = CPU_SAMPLE_TASKS * len(times) / total
@@ -1204,14 +1209,19 @@ def run_ours(args, dist):
         parzen = run_parzen(dev, traffic, with_cpu=(world == 1 and not args.skip_cpu))
     if rank == 0 and world == 1 and not args.skip_cpu:
         cores = os.cpu_count() or 1
-        res_c, kind = cpu_arm("pi", cores, reps=3, warm=1)
-        best = min(res_c["times"])
-        cpu = {"value": CPU_SAMPLE_TASKS / best, "unit": "tasks/s", "cores": cores, "kind": kind, "impl": res_c.get("impl"),
-               "sample": "best of 3 Pool(processes=%d).map over %d pi_inside_det tasks (C body via ctypes), default chunksize 32, "
-                         "after a 1000-task warm-up map" % (cores, CPU_SAMPLE_TASKS),
-               "mean_tasks_per_s": CPU_SAMPLE_TASKS * len(res_c["times"]) / sum(res_c["times"])}
-        assert res_c["count"] == cref_count_first_1e6(0)
         try:
+            res_c, kind = cpu_arm("pi", cores, reps=3, warm=1)
+            best = min(res_c["times"])
+            cpu = {"value": CPU_SAMPLE_TASKS / best, "unit": "tasks/s", "cores": cores, "kind": kind, "impl": res_c.get("impl"),
+                   "sample": "best of 3 Pool(processes=%d).map over %d pi_inside_det tasks (C body via ctypes), default chunksize 32, "
+                             "after a 1000-task warm-up map" % (cores, CPU_SAMPLE_TASKS),
+                   "mean_tasks_per_s": CPU_SAMPLE_TASKS * len(res_c["times"]) / sum(res_c["times"]),
+                   "count_matches_oracle": res_c["count"] == cref_count_first_1e6(0)}
+        except Exception as e:      # noqa: BLE001 -- the GPU line must not be lost to a hiccup of the CPU arm
+            cpu = {"value": None, "unit": "tasks/s", "cores": cores, "kind": "unavailable", "sample": str(e)[:300]}
+        try:
+            if cpu["value"] is None:
+                raise RuntimeError("CPU arm unavailable")
             r4, k4 = cpu_arm("pi", 4, reps=2, warm=0)
             cpu["pool4"] = {"value": CPU_SAMPLE_TASKS / min(r4["times"]), "unit": "tasks/s", "cores": 4, "kind": k4,
                             "sample": "best of 2 Pool(4).map over %d tasks (examples/pi_estimation.py:15, BASELINE.json configs[0])" % CPU_SAMPLE_TASKS}
