@@ -282,7 +282,7 @@ class MapResult:
 
     def _raise_task_error(self, res):
         code, task = res.err_code, res.err_task
-        name = self._spec.name
+        name = getattr(self, "_user_spec", self._spec).name     # the body the caller mapped (not its bit-packed twin)
         if code == _abi.FBR_TASK_OVERFLOW:
             raise OverflowError("%s: result of task %d does not fit int64 (Python ints are unbounded; "
                                 "the device body refuses to wrap)" % (name, task))
