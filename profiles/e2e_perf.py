@@ -9,7 +9,7 @@ import fiber_b200  # noqa: E402
 from examples import workloads as W  # noqa: E402
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
-for mode in ("host", "device", "bits"):
+for mode in ("host", "bytes", "device"):      # host: bool results one bit each, stored zero-copy; bytes: one byte each
     pool = fiber_b200.Pool(1, results=mode)
     r = range(10 ** 8)
     for _ in range(3):

@@ -22,6 +22,6 @@ for i in range(steps + 3):
 st = eng.stats()
 print("%s occ=%s unit=%s  dispatch %.4f ms  gather %.4f ms  count %d" % (
     body, os.environ.get("FBR_DISPATCH_OCC", "-"), os.environ.get("FBR_UNIT_TASKS", "-"),
-    st["dispatch_ms"] / st["dispatch_launches"], st["gather_ms"] / st["gather_launches"], cnt), flush=True)
+    st["dispatch_ms"] / st["dispatch_launches"], st["gather_ms"] / max(1, st["gather_launches"]), cnt), flush=True)   # direct placement: no gather
 eng.dfree(out)
 eng.close()
