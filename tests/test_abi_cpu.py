@@ -329,3 +329,23 @@ def test_initializer_binding_and_result_layout_options():
     xs, px = np.zeros((4, 2)), np.zeros((2, 1))
     with pytest.raises(TypeError):
         s.encode_starmap([(0.5,), (xs, px, 0.7)])
+
+
+def test_parzen_block_cache_and_isolation_argument():
+    """The parzen encoder re-uses the broadcast block of the previous call when the arrays compare equal (the example
+    issues 102 apply_async calls with the same 160 KB array) and rebuilds it when they do not; Pool validates `isolation`."""
+    s = registry.spec("parzen_f32")
+    xs, px = np.random.default_rng(0).standard_normal((500, 2)), np.zeros((2, 1))
+    b1 = s.shared_block(xs, px)
+    assert s.shared_block(xs.copy(), px.copy()) is b1             # equal content: the very same bytes object
+    xs2 = xs.copy()
+    xs2[17, 1] += 1.0
+    b2 = s.shared_block(xs2, px)
+    assert b2 is not b1 and b2 != b1 and len(b2) == len(b1) == 80 + 500 * 2 * 4
+    assert s.shared_block(xs, px) == b1                            # and back again (rebuilt, same content)
+    e = s.encode_apply((xs, px, 0.5), {})
+    assert e.n == 1 and e.shared is s.shared_block(xs, px)
+    with pytest.raises(ValueError, match="isolation"):
+        fiber_b200.Pool(2, isolation="container")
+    p = fiber_b200.Pool(2, error_handling=True, isolation="process")
+    assert p._isolation == "process" and p._proc is None          # worker processes start lazily, like the reference's
