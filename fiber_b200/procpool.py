@@ -127,7 +127,7 @@ def gpu_worker_main(device, conn, results, sys_path):
                 finally:
                     os._exit(3)
             conn.send(("error", job, blk, "EngineError", str(e)))
-        except (OverflowError, ValueError, TypeError, RuntimeError, KeyError) as e:
+        except (OverflowError, ValueError, TypeError, RuntimeError, KeyError, OSError) as e:   # OSError: the segment of a failed map is gone
             conn.send(("error", job, blk, type(e).__name__, str(e)))
     os._exit(0)
 
@@ -155,6 +155,8 @@ class _Job:
         self.nbytes = nbytes
         self.sum, self.error = 0, None
         self.event = threading.Event()
+        if self.shm is not None:            # the /dev/shm name never outlives the job object (fire-and-forget maps, failed maps)
+            weakref.finalize(self, _release_shm, self.shm)
 
     def offset(self, lo):
         return lo // 8 if self.bits else lo * self.result_bytes
@@ -189,8 +191,8 @@ class ProcessResult:
                 arr = job.shm.array[:job.nbytes].view(dtype).reshape((job.n,) + sub)
                 self._result = ResultArray(self._spec, arr, total)
             if job.shm is not None:
-                self._result._shm = job.shm
-                weakref.finalize(self._result, _release_shm, job.shm)
+                self._result._shm = job.shm      # the mapping lives as long as the result; workers are done with the name
+                job.shm.release()
         return self._result[0] if self._single else self._result
 
 
@@ -273,6 +275,7 @@ class ProcessPool:
         job.error = exc
         job.blocks.clear()
         job.event.set()
+        # (the segment's name is unlinked when the job object goes away: blocks of this map may still be running)
 
     def _on_death(self, w, reason):
         self.stats["workers_lost"] += 1
