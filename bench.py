@@ -221,9 +221,13 @@ class Dist:
         # belongs to the path (count fold, scatter / gather of blocks); torch.distributed only bootstraps it
         # (its c10d store publishes the 128-byte id) and provides the barrier of the timing bracket
         self.comm = None
+        self.comm_error = None
         if self.world > 1 and backend == "nccl":
             from fiber_b200 import comm as C
-            self.comm = C.Comm.from_store(dist.distributed_c10d._get_default_store(), self.local_rank, self.world, self.rank)
+            try:
+                self.comm = C.Comm.from_store(dist.distributed_c10d._get_default_store(), self.local_rank, self.world, self.rank)
+            except Exception as e:      # noqa: BLE001 -- e.g. no loadable NCCL build: the exchanges fall back to torch.distributed
+                self.comm, self.comm_error = None, "%s: %s" % (type(e).__name__, e)
 
     def barrier(self):
         if self.world > 1:
@@ -700,6 +704,13 @@ def run_multi_gpu(args, dist, dev):
     def scattered_map():
         # fan-out and fan-in of the reference's master sockets (fiber/pool.py:910-920) as grouped ncclSend/ncclRecv
         # issued by the engine's communicator; the map in between is the shard-resident one
+        if comm is None:            # engine communicator unavailable (see Dist): same exchange through torch.distributed
+            td.scatter(inp, list(full_in.chunk(world)) if rank == 0 else None, src=0)
+            torch.cuda.synchronize()
+            local_map()
+            td.gather(out, list(full_out.chunk(world)) if rank == 0 else None, dst=0)
+            torch.cuda.synchronize()
+            return
         comm.scatter(full_in if rank == 0 else None, inp, blk_bytes, root=0)
         comm.sync()
         local_map()
@@ -741,8 +752,11 @@ def run_multi_gpu(args, dist, dev):
         store.wait(["fbr_fused_done"])
     dist.barrier()
     from fiber_b200 import comm as C
-    ar_ok, algbw, busbw, ar_ms = C.allreduce_bench(comm, 64 * 1024 * 1024, steps=max(5, args.steps), warmup=3)
     t_ok, t_algbw, t_busbw, t_ms = allreduce_bench(64 * 1024 * 1024, steps=max(5, args.steps), warmup=3, device=cuda)
+    if comm is not None:
+        ar_ok, algbw, busbw, ar_ms = C.allreduce_bench(comm, 64 * 1024 * 1024, steps=max(5, args.steps), warmup=3)
+    else:
+        ar_ok, algbw, busbw, ar_ms = t_ok, t_algbw, t_busbw, t_ms
     return {
         "payload4k_sharded": {
             "workload": "synthetic 4 KB-payload map, %d tasks TOTAL in contiguous blocks over %d GPUs (BASELINE.json configs[3])" % (n_total, world),
@@ -757,7 +771,8 @@ def run_multi_gpu(args, dist, dev):
         "inprocess_pool_e2e": inproc,
         "ring_allreduce": {"workload": "all-reduce SUM of 64 Mi fp32 (256 MiB) per rank, %d ranks (BASELINE.json configs[4])" % world,
                            "bit_exact": ar_ok, "algbw_GBps": algbw, "busbw_GBps": busbw, "ms": ar_ms,
-                           "api": "fbr_comm_allreduce (ncclAllReduce behind the C ABI, bootstrap id from the ring member table)",
+                           "api": "fbr_comm_allreduce (ncclAllReduce behind the C ABI, bootstrap id from the ring member table)"
+                                  if comm is not None else "torch.distributed (engine communicator unavailable: %s)" % dist.comm_error,
                            "torch_distributed_same_buffer": {"bit_exact": t_ok, "busbw_GBps": t_busbw, "ms": t_ms},
                            "nvlink_ref": "measured refs: 725 GB/s all-reduce busbw @1 GiB, 770 GB/s peer copy (B200_PROFILING.md)"},
     }
